@@ -1,0 +1,160 @@
+/* usrt.h -- C ABI of libusrt_b200.so: the B200-native (sm_100a) LBVH build + ray-cast path that
+ * replaces UnitySimpleRaytracing's HLSL compute kernels and their C# dispatch layer.
+ *
+ * Boundary. Every entry point below stands in for one reference entry point; the
+ * citation is the reference file:line it replaces (paths relative to the reference repo root).
+ * Buffer layouts are the reference's, byte for byte (Assets/_Shaders/Constants.cginc:9-54,
+ * Assets/_Scripts/SceneDataTypes.cs:4-90).
+ *
+ * Conventions
+ *   - plain C, pointers and sizes only; every function returns 0 on success or a negative
+ *     usrt_status; usrt_last_error(ctx) gives the message. Nothing aborts, nothing falls back to a
+ *     CPU path: without a CUDA device usrt_create fails with USRT_ERR_CUDA.
+ *   - a context owns all device memory and one CUDA stream. Calls enqueue on that stream and are
+ *     asynchronous unless they take or return HOST data (upload/download/..._host), which
+ *     synchronise. A context is not thread-safe; distinct contexts (one per GPU) are independent.
+ *   - host pointers are caller-owned and only touched during the call.
+ */
+#ifndef USRT_H
+#define USRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- struct layouts: Constants.cginc:9-54 / SceneDataTypes.cs:4-90 --------------------------- */
+typedef struct usrt_aabb { float min[3]; float _dummy0; float max[3]; float _dummy1; } usrt_aabb;            /* 32 B */
+typedef struct usrt_internal_node {                                                                           /* 24 B */
+    uint32_t leftNode, leftNodeType, rightNode, rightNodeType, parent, index;
+} usrt_internal_node;
+typedef struct usrt_leaf_node { uint32_t parent, index; } usrt_leaf_node;                                     /*  8 B */
+typedef struct usrt_triangle {                                                                                /* 128 B */
+    float a[3], _dummy0, b[3], _dummy1, c[3], _dummy2;
+    float a_uv[2], b_uv[2], c_uv[2], _dummy3[2];
+    float a_normal[3], _dummy4, b_normal[3], _dummy5, c_normal[3], _dummy6;
+} usrt_triangle;
+/* Raytracing.compute:30-35 -- the hit record. Miss = { (float)0x7F7FFFFF, 0, (0,0) } (Constants.cginc:7). */
+typedef struct usrt_raycast_result { float distance; uint32_t triangleIndex; float uv[2]; } usrt_raycast_result; /* 16 B */
+
+#define USRT_INTERNAL_NODE 0u          /* Constants.cginc:17 */
+#define USRT_LEAF_NODE 1u              /* Constants.cginc:18 */
+#define USRT_NULL 0xFFFFFFFFu          /* SceneDataTypes.cs:63-89 NullLeaf; MeshBufferContainer.cs:108-109 padding */
+
+typedef enum usrt_status {
+    USRT_OK = 0,
+    USRT_ERR_ARG = -1,        /* bad argument (null pointer, n > capacity, n < 2 for the tree, ...) */
+    USRT_ERR_CUDA = -2,       /* a CUDA runtime call or kernel failed; see usrt_last_error */
+    USRT_ERR_STATE = -3,      /* stage called before the stage it depends on */
+    USRT_ERR_NOMEM = -4
+} usrt_status;
+
+/* The seven scene buffers MeshBufferContainer owns (MeshBufferContainer.cs:87-94), by name. */
+typedef enum usrt_buffer {
+    USRT_BUF_KEYS = 0,            /* uint32[capacity]  _keysBuffer (Morton, later sorted, later distributed) */
+    USRT_BUF_TRIANGLE_INDEX = 1,  /* uint32[capacity]  _triangleIndexBuffer (sorted triangle ids) */
+    USRT_BUF_TRIANGLE_DATA = 2,   /* usrt_triangle[capacity] */
+    USRT_BUF_TRIANGLE_AABB = 3,   /* usrt_aabb[capacity] */
+    USRT_BUF_BVH_DATA = 4,        /* usrt_aabb[capacity]  internal-node boxes */
+    USRT_BUF_LEAF_NODES = 5,      /* usrt_leaf_node[capacity] */
+    USRT_BUF_INTERNAL_NODES = 6,  /* usrt_internal_node[capacity] */
+    USRT_BUF_COUNT = 7
+} usrt_buffer;
+
+typedef struct usrt_context usrt_context;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Replaces the fixed 2^19-slot allocation of MeshBufferContainer.cs:108-115 / Constants.cs:3-6 with
+ * a runtime capacity. Keys/indices are filled with 0xFFFFFFFF, node buffers with NullLeaf. */
+int usrt_create(int device, uint32_t capacity, usrt_context** out);
+int usrt_destroy(usrt_context* ctx);                    /* MeshBufferContainer.Dispose :207-216 */
+const char* usrt_last_error(const usrt_context* ctx);   /* stands in for Debug.LogError strings */
+const char* usrt_version(void);
+int usrt_sync(usrt_context* ctx);
+/* Enqueue on an existing CUDA stream (e.g. torch's current stream) instead of the context's own. */
+int usrt_set_stream(usrt_context* ctx, void* cuda_stream);
+/* World box of NormalizeCentroid, default -125/+125 (MeshBufferContainer.cs:9-15). */
+int usrt_set_world_bounds(usrt_context* ctx, float whole_min, float whole_max);
+uint32_t usrt_capacity(const usrt_context* ctx);
+uint32_t usrt_triangles_length(const usrt_context* ctx);   /* MeshBufferContainer.TrianglesLength :30 */
+
+/* ---- MeshBufferContainer(Mesh) : MeshBufferContainer.cs:96-152 --------------------------------- */
+/* Copy n packed triangles to the device (synchronous) and re-initialise keys/indices/nodes as the
+ * constructor does (:108-115). Does not compute Morton codes; see usrt_morton. */
+int usrt_upload_triangles(usrt_context* ctx, const usrt_triangle* host_triangles, uint32_t n);
+/* Same, from a DEVICE pointer (async, device-to-device). */
+int usrt_set_triangles_device(usrt_context* ctx, const void* dev_triangles, uint32_t n);
+/* K1 -- the CPU loop of MeshBufferContainer.cs:123-146 as a kernel: padded AABB, centroid of the padded
+ * box, NormalizeCentroid, Morton3D; keys[i], triangleIndex[i] = i, triangleAABB[i]. */
+int usrt_morton(usrt_context* ctx);
+
+/* ---- ComputeBufferSorter<uint,uint>.Sort() : ComputeBufferSorter.cs:100-126 -------------------- */
+/* K2 -- stable ascending LSD radix sort, 4 passes x 8 bits over all 32 key bits, of the context's
+ * (keys, triangleIndex) pairs [0, trianglesLength). Padding slots keep 0xFFFFFFFF. */
+int usrt_sort(usrt_context* ctx);
+/* Standalone sorter on caller data (ComputeBufferSorter ctor :44 takes arbitrary key/value buffers).
+ * In place. _device: pointers are device memory of this context's GPU, async. _host: synchronous. */
+int usrt_sort_pairs_device(usrt_context* ctx, uint32_t* dev_keys, uint32_t* dev_values, uint64_t count);
+int usrt_sort_pairs_host(usrt_context* ctx, uint32_t* host_keys, uint32_t* host_values, uint64_t count);
+/* One stable partition pass by an arbitrary 8-bit digit (bit_offset in 0..24) from src to dst; used
+ * as the bucket-split step of the multi-GPU sort. histogram_out (device, 256 x uint32) may be NULL. */
+int usrt_partition_pass_device(usrt_context* ctx, const uint32_t* src_keys, const uint32_t* src_values,
+                               uint32_t* dst_keys, uint32_t* dst_values, uint64_t count, int bit_offset,
+                               uint32_t* histogram_out);
+
+/* ---- MeshBufferContainer.DistributeKeys() : MeshBufferContainer.cs:154-169 -------------------- */
+/* K3 -- new[0]=0; new[i]=new[i-1]+max(k[i]-k[i-1],1) in wrapping uint32 over [0, trianglesLength). */
+int usrt_distribute_keys(usrt_context* ctx);
+
+/* ---- BVHConstructor : BVHConstructor.cs:24-69 ---------------------------------------------- */
+/* K4 -- ConstructTree() :61-64 -> kernel TreeConstructor (BVH.compute:94-149). Needs n >= 2. */
+int usrt_construct_tree(usrt_context* ctx);
+/* K5 -- ConstructBVH() :66-69 -> kernel BVHConstructor (BVH.compute:172-220). Re-runnable: the
+ * counter buffer (BVHConstructor.cs:41) is self-resetting. Also emits the traversal-side packed
+ * node/triangle arrays the trace kernels read. */
+int usrt_construct_bvh(usrt_context* ctx);
+/* RaytracingMeshDrawer.Awake() :34-51 as one enqueue: K1 -> K2 -> K3 -> K4 -> K5, no host sync. */
+int usrt_rebuild(usrt_context* ctx);
+/* Device time of the last usrt_rebuild, per stage, in ms: morton, sort, distribute, tree, bvh, total.
+ * Synchronises. Only filled when timing was enabled before the rebuild. */
+int usrt_enable_stage_timing(usrt_context* ctx, int enabled);
+int usrt_last_rebuild_ms(usrt_context* ctx, float out_ms[6]);
+
+/* ---- Dispatch(Raytracing) : RaytracingMeshDrawer.cs:76-84, Raytracing.compute:105-176 ---------- */
+/* K6 -- one hit record per pixel, index y*width + x, row 0 = most negative camera-space y.
+ * near = _ProjectionParams.y; tan_half_fov = tan(fovDeg*Deg2Rad/2) (RaytracingMeshDrawer.cs:80);
+ * camera_to_world: 16 floats ROW-major (m[r*4+c]); Unity's Matrix4x4 fields m{r}{c} map directly.
+ * Rows [y0, y1) only are traced (y0=0,y1=height for a full frame) -- the ray-sharding hook.
+ * host_out (may be NULL) receives rows [y0,y1) at their frame positions, i.e. host_out + y0*width;
+ * the device copy stays readable through usrt_hits_device. */
+int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
+                       const float camera_to_world[16], int y0, int y1, usrt_raycast_result* host_out);
+/* Same traversal for caller rays: 8 floats per ray (origin.xyz, pad, dir.xyz, pad); dir is used as
+ * given, inv_dir = 1/dir. */
+int usrt_trace_rays(usrt_context* ctx, const float* host_rays, uint64_t num_rays, usrt_raycast_result* host_out);
+int usrt_trace_rays_device(usrt_context* ctx, const void* dev_rays, uint64_t num_rays, void* dev_out);
+/* Device pointer of the hit records written by the last trace call (usrt_raycast_result[]). */
+int usrt_hits_device(usrt_context* ctx, void** dev_ptr, uint64_t* count);
+/* 0 = strict (default): the reference's visiting semantics exactly -- every box the ray line touches
+ * is visited, no distance culling. 1 = culled: skips boxes entirely beyond the current closest hit;
+ * NOT part of the parity contract (reported separately). */
+int usrt_set_trace_mode(usrt_context* ctx, int mode);
+
+/* ---- DataBuffer<T>.GetData() : DataBuffer.cs:50-54 ------------------------------------------- */
+/* Copy `count` elements of a scene buffer to host memory (synchronous). */
+int usrt_download(usrt_context* ctx, int buffer /* usrt_buffer */, void* host_dst, uint64_t count);
+/* Raw device pointer of a scene buffer (for zero-copy interop, e.g. torch / NCCL broadcast). The
+ * KEYS pointer can change after usrt_sort / usrt_distribute_keys (ping-pong); re-query it. */
+int usrt_device_ptr(usrt_context* ctx, int buffer /* usrt_buffer */, void** dev_ptr);
+/* Validator of MeshBufferContainer.GetAllGpuData :181-195 on the device: counts leaf [0,n) and
+ * internal [0,n-1) entries that still equal NullLeaf. */
+int usrt_count_corrupted_nodes(usrt_context* ctx, uint32_t* leaf_corrupted, uint32_t* internal_corrupted);
+
+/* Number of kernels this library has launched on the context since creation (bench bookkeeping). */
+uint64_t usrt_kernel_launches(const usrt_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USRT_H */

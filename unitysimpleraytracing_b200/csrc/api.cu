@@ -1,0 +1,532 @@
+// api.cu -- the extern "C" boundary of libusrt_b200.so (declared in include/usrt.h): context and
+// buffer ownership, stage sequencing, host<->device copies. It replaces the reference's C# dispatch
+// layer: MeshBufferContainer.cs (buffers, Morton, DistributeKeys), ComputeBufferSorter.cs (Sort),
+// BVHConstructor.cs (ConstructTree / ConstructBVH), DataBuffer.cs (GetData / Sync) and the build +
+// trace sequence of RaytracingMeshDrawer.cs:30-54,76-84.
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "usrt_internal.cuh"
+
+using namespace usrt;
+
+enum Stage : uint32_t { ST_TRIS = 1, ST_MORTON = 2, ST_SORTED = 4, ST_DISTRIBUTED = 8, ST_TREE = 16, ST_BVH = 32 };
+
+struct usrt_context {
+    int device = 0;
+    uint32_t capacity = 0;
+    uint32_t n = 0;                       // trianglesLength
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    float whole_min = -125.0f, whole_max = 125.0f;   // MeshBufferContainer.cs:9-15
+    uint32_t stage = 0;
+
+    // the seven scene buffers of MeshBufferContainer.cs:87-94 (+ ping-pong partners for keys/indices)
+    uint32_t *keys = nullptr, *keys_alt = nullptr;
+    uint32_t *tri_index = nullptr, *tri_index_alt = nullptr;
+    usrt_triangle* triangles = nullptr;
+    usrt_aabb* tri_aabb = nullptr;
+    usrt_aabb* bvh = nullptr;
+    usrt_leaf_node* leaf = nullptr;
+    usrt_internal_node* internal = nullptr;
+    // BVHConstructor.cs:16 _atomics
+    uint32_t* counters = nullptr;
+    // traversal-side arrays written by K5
+    float4* packed_nodes = nullptr;
+    float4* packed_tris = nullptr;
+    // scratch
+    SortScratch sort;
+    void* scan_status = nullptr;
+    uint32_t* small = nullptr;            // a few device words (validators)
+    // trace
+    usrt_raycast_result* hits = nullptr;
+    uint64_t hits_capacity = 0, hits_count = 0;
+    float4* rays = nullptr;
+    uint64_t rays_capacity = 0;
+    int trace_mode = 0;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+
+    uint64_t launches = 0;
+    char err[512] = {0};
+};
+
+namespace {
+
+int fail(usrt_context* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(ctx, call)                                                                                        \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? USRT_ERR_NOMEM : USRT_ERR_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e__));                                                            \
+    } while (0)
+
+#define NEED_CTX(ctx)                 \
+    do {                              \
+        if (!(ctx)) return USRT_ERR_ARG; \
+    } while (0)
+
+int bind_device(usrt_context* ctx) {
+    CU(ctx, cudaSetDevice(ctx->device));
+    return USRT_OK;
+}
+
+// MeshBufferContainer.cs:108-115: keys/indices = uint.MaxValue, leaf/internal = NullLeaf (all 0xFF).
+int reset_scene_buffers(usrt_context* ctx) {
+    const size_t c = ctx->capacity;
+    CU(ctx, cudaMemsetAsync(ctx->keys, 0xFF, c * 4, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->keys_alt, 0xFF, c * 4, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->tri_index, 0xFF, c * 4, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->tri_index_alt, 0xFF, c * 4, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->leaf, 0xFF, c * sizeof(usrt_leaf_node), ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->internal, 0xFF, c * sizeof(usrt_internal_node), ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->tri_aabb, 0, c * sizeof(usrt_aabb), ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->bvh, 0, c * sizeof(usrt_aabb), ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->counters, 0, c * 4, ctx->stream));          // BVHConstructor.cs:41
+    return USRT_OK;
+}
+
+int ensure_hits(usrt_context* ctx, uint64_t count) {
+    if (count > ctx->hits_capacity) {
+        if (ctx->hits) CU(ctx, cudaFree(ctx->hits));
+        ctx->hits = nullptr; ctx->hits_capacity = 0;
+        CU(ctx, cudaMalloc(&ctx->hits, count * sizeof(usrt_raycast_result)));
+        ctx->hits_capacity = count;
+    }
+    return USRT_OK;
+}
+
+int ensure_rays(usrt_context* ctx, uint64_t count) {
+    if (count > ctx->rays_capacity) {
+        if (ctx->rays) CU(ctx, cudaFree(ctx->rays));
+        ctx->rays = nullptr; ctx->rays_capacity = 0;
+        CU(ctx, cudaMalloc(&ctx->rays, count * 2 * sizeof(float4)));
+        ctx->rays_capacity = count;
+    }
+    return USRT_OK;
+}
+
+int do_morton(usrt_context* ctx) {
+    CU(ctx, launch_morton(ctx->triangles, ctx->n, ctx->whole_min, ctx->whole_max, ctx->keys, ctx->tri_index,
+                          ctx->tri_aabb, ctx->stream));
+    ctx->launches += 1;
+    ctx->stage = ST_TRIS | ST_MORTON;
+    return USRT_OK;
+}
+
+int do_sort(usrt_context* ctx) {
+    CU(ctx, sort_pairs(ctx->keys, ctx->tri_index, ctx->keys_alt, ctx->tri_index_alt, ctx->n, ctx->sort, ctx->stream,
+                       &ctx->launches));
+    ctx->stage |= ST_SORTED;
+    return USRT_OK;
+}
+
+int do_distribute(usrt_context* ctx) {
+    int l = 0;
+    CU(ctx, launch_distribute_keys(ctx->keys, ctx->keys_alt, ctx->n, ctx->scan_status, ctx->stream, &l));
+    ctx->launches += l;
+    std::swap(ctx->keys, ctx->keys_alt);        // the distributed keys ARE the keys buffer from here on
+    ctx->stage |= ST_DISTRIBUTED;
+    return USRT_OK;
+}
+
+int do_tree(usrt_context* ctx) {
+    CU(ctx, launch_construct_tree(ctx->keys, ctx->n, ctx->internal, ctx->leaf, ctx->stream));
+    ctx->launches += 1;
+    ctx->stage |= ST_TREE;
+    return USRT_OK;
+}
+
+int do_bvh(usrt_context* ctx) {
+    CU(ctx, launch_construct_bvh(ctx->n, ctx->tri_index, ctx->tri_aabb, ctx->triangles, ctx->internal, ctx->leaf,
+                                 ctx->bvh, ctx->counters, ctx->packed_nodes, ctx->packed_tris, ctx->stream));
+    ctx->launches += 1;
+    ctx->stage |= ST_BVH;
+    return USRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* usrt_version(void) { return "usrt_b200 0.1 (sm_100a)"; }
+
+int usrt_create(int device, uint32_t capacity, usrt_context** out) {
+    if (!out || capacity < 2 || capacity > 0x7FFFFFFFu) return USRT_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) return USRT_ERR_CUDA;   // no CPU fallback, by design
+    usrt_context* ctx = new (std::nothrow) usrt_context();
+    if (!ctx) return USRT_ERR_NOMEM;
+    ctx->device = device;
+    ctx->capacity = capacity;
+    int rc = USRT_OK;
+    auto init = [&]() -> int {
+        CU(ctx, cudaSetDevice(device));
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
+        const size_t c = capacity;
+        CU(ctx, cudaMalloc(&ctx->keys, c * 4));
+        CU(ctx, cudaMalloc(&ctx->keys_alt, c * 4));
+        CU(ctx, cudaMalloc(&ctx->tri_index, c * 4));
+        CU(ctx, cudaMalloc(&ctx->tri_index_alt, c * 4));
+        CU(ctx, cudaMalloc(&ctx->triangles, c * sizeof(usrt_triangle)));
+        CU(ctx, cudaMalloc(&ctx->tri_aabb, c * sizeof(usrt_aabb)));
+        CU(ctx, cudaMalloc(&ctx->bvh, c * sizeof(usrt_aabb)));
+        CU(ctx, cudaMalloc(&ctx->leaf, c * sizeof(usrt_leaf_node)));
+        CU(ctx, cudaMalloc(&ctx->internal, c * sizeof(usrt_internal_node)));
+        CU(ctx, cudaMalloc(&ctx->counters, c * 4));
+        CU(ctx, cudaMalloc(&ctx->packed_nodes, c * 4 * sizeof(float4)));
+        CU(ctx, cudaMalloc(&ctx->packed_tris, c * 3 * sizeof(float4)));
+        CU(ctx, cudaMalloc(&ctx->scan_status, distribute_status_bytes(capacity)));
+        CU(ctx, cudaMalloc(&ctx->small, 64));
+        CU(ctx, sort_scratch_reserve(ctx->sort, capacity, false));
+        CU(ctx, cudaMemsetAsync(ctx->triangles, 0, c * sizeof(usrt_triangle), ctx->stream));
+        for (auto& ev : ctx->ev) CU(ctx, cudaEventCreate(&ev));
+        int r = reset_scene_buffers(ctx);
+        if (r != USRT_OK) return r;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return USRT_OK;
+    };
+    rc = init();
+    if (rc != USRT_OK) {
+        fprintf(stderr, "usrt_create failed: %s\n", ctx->err);
+        usrt_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return USRT_OK;
+}
+
+int usrt_destroy(usrt_context* ctx) {
+    NEED_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    void* ptrs[] = {ctx->keys, ctx->keys_alt, ctx->tri_index, ctx->tri_index_alt, ctx->triangles, ctx->tri_aabb,
+                    ctx->bvh, ctx->leaf, ctx->internal, ctx->counters, ctx->packed_nodes, ctx->packed_tris,
+                    ctx->scan_status, ctx->small, ctx->hits, ctx->rays};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    sort_scratch_free(ctx->sort);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return USRT_OK;
+}
+
+const char* usrt_last_error(const usrt_context* ctx) { return ctx ? ctx->err : "null context"; }
+
+int usrt_sync(usrt_context* ctx) {
+    NEED_CTX(ctx);
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return USRT_OK;
+}
+
+int usrt_set_stream(usrt_context* ctx, void* cuda_stream) {
+    NEED_CTX(ctx);
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return USRT_OK;
+}
+
+int usrt_set_world_bounds(usrt_context* ctx, float whole_min, float whole_max) {
+    NEED_CTX(ctx);
+    if (!(whole_max > whole_min)) return fail(ctx, USRT_ERR_ARG, "world bounds: max must exceed min");
+    ctx->whole_min = whole_min;
+    ctx->whole_max = whole_max;
+    return USRT_OK;
+}
+
+uint32_t usrt_capacity(const usrt_context* ctx) { return ctx ? ctx->capacity : 0; }
+uint32_t usrt_triangles_length(const usrt_context* ctx) { return ctx ? ctx->n : 0; }
+uint64_t usrt_kernel_launches(const usrt_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int usrt_upload_triangles(usrt_context* ctx, const usrt_triangle* host_triangles, uint32_t n) {
+    NEED_CTX(ctx);
+    if (!host_triangles || n > ctx->capacity) return fail(ctx, USRT_ERR_ARG, "upload_triangles: n=%u capacity=%u", n, ctx->capacity);
+    if (int r = bind_device(ctx)) return r;
+    if (int r = reset_scene_buffers(ctx)) return r;
+    CU(ctx, cudaMemcpyAsync(ctx->triangles, host_triangles, (size_t)n * sizeof(usrt_triangle), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n = n;
+    ctx->stage = ST_TRIS;
+    return USRT_OK;
+}
+
+int usrt_set_triangles_device(usrt_context* ctx, const void* dev_triangles, uint32_t n) {
+    NEED_CTX(ctx);
+    if (!dev_triangles || n > ctx->capacity) return fail(ctx, USRT_ERR_ARG, "set_triangles_device: n=%u capacity=%u", n, ctx->capacity);
+    if (int r = bind_device(ctx)) return r;
+    if (int r = reset_scene_buffers(ctx)) return r;
+    CU(ctx, cudaMemcpyAsync(ctx->triangles, dev_triangles, (size_t)n * sizeof(usrt_triangle), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->n = n;
+    ctx->stage = ST_TRIS;
+    return USRT_OK;
+}
+
+int usrt_morton(usrt_context* ctx) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_TRIS)) return fail(ctx, USRT_ERR_STATE, "morton: no triangles uploaded");
+    if (int r = bind_device(ctx)) return r;
+    return do_morton(ctx);
+}
+
+int usrt_sort(usrt_context* ctx) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_MORTON)) return fail(ctx, USRT_ERR_STATE, "sort: keys not generated (call usrt_morton)");
+    if (int r = bind_device(ctx)) return r;
+    return do_sort(ctx);
+}
+
+int usrt_sort_pairs_device(usrt_context* ctx, uint32_t* dev_keys, uint32_t* dev_values, uint64_t count) {
+    NEED_CTX(ctx);
+    if (count && !dev_keys) return fail(ctx, USRT_ERR_ARG, "sort_pairs: null keys");
+    if (count >= (1ull << 32)) return fail(ctx, USRT_ERR_ARG, "sort_pairs: count must be < 2^32");
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, sort_scratch_reserve(ctx->sort, std::max<uint64_t>(count, 1), true));
+    CU(ctx, sort_pairs(dev_keys, dev_values, ctx->sort.keys_alt, dev_values ? ctx->sort.vals_alt : nullptr, count,
+                       ctx->sort, ctx->stream, &ctx->launches));
+    return USRT_OK;
+}
+
+int usrt_sort_pairs_host(usrt_context* ctx, uint32_t* host_keys, uint32_t* host_values, uint64_t count) {
+    NEED_CTX(ctx);
+    if (count == 0) return USRT_OK;
+    if (!host_keys) return fail(ctx, USRT_ERR_ARG, "sort_pairs_host: null keys");
+    if (count >= (1ull << 32)) return fail(ctx, USRT_ERR_ARG, "sort_pairs: count must be < 2^32");
+    if (int r = bind_device(ctx)) return r;
+    uint32_t *dk = nullptr, *dv = nullptr;
+    CU(ctx, cudaMalloc(&dk, count * 4));
+    if (host_values) {
+        cudaError_t e = cudaMalloc(&dv, count * 4);
+        if (e != cudaSuccess) { cudaFree(dk); return fail(ctx, USRT_ERR_NOMEM, "sort_pairs_host: %s", cudaGetErrorString(e)); }
+    }
+    int rc = USRT_OK;
+    auto run = [&]() -> int {
+        CU(ctx, cudaMemcpyAsync(dk, host_keys, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (dv) CU(ctx, cudaMemcpyAsync(dv, host_values, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (int r = usrt_sort_pairs_device(ctx, dk, dv, count)) return r;
+        CU(ctx, cudaMemcpyAsync(host_keys, dk, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dv) CU(ctx, cudaMemcpyAsync(host_values, dv, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return USRT_OK;
+    };
+    rc = run();
+    cudaFree(dk);
+    if (dv) cudaFree(dv);
+    return rc;
+}
+
+int usrt_partition_pass_device(usrt_context* ctx, const uint32_t* src_keys, const uint32_t* src_values,
+                               uint32_t* dst_keys, uint32_t* dst_values, uint64_t count, int bit_offset,
+                               uint32_t* histogram_out) {
+    NEED_CTX(ctx);
+    if (bit_offset < 0 || bit_offset > 24 || (bit_offset & 7)) return fail(ctx, USRT_ERR_ARG, "partition_pass: bit_offset must be 0, 8, 16 or 24");
+    if (count && (!src_keys || !dst_keys)) return fail(ctx, USRT_ERR_ARG, "partition_pass: null keys");
+    if (count >= (1ull << 32)) return fail(ctx, USRT_ERR_ARG, "partition_pass: count must be < 2^32");
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, partition_pass(src_keys, src_values, dst_keys, dst_values, count, bit_offset, histogram_out, ctx->sort,
+                           ctx->stream, &ctx->launches));
+    return USRT_OK;
+}
+
+int usrt_distribute_keys(usrt_context* ctx) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_SORTED)) return fail(ctx, USRT_ERR_STATE, "distribute_keys: keys not sorted (call usrt_sort)");
+    if (ctx->stage & ST_DISTRIBUTED) return fail(ctx, USRT_ERR_STATE, "distribute_keys: already applied to these keys");
+    if (int r = bind_device(ctx)) return r;
+    return do_distribute(ctx);
+}
+
+int usrt_construct_tree(usrt_context* ctx) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_SORTED)) return fail(ctx, USRT_ERR_STATE, "construct_tree: keys not sorted");
+    if (ctx->n < 2) return fail(ctx, USRT_ERR_ARG, "construct_tree: trianglesCount=%u; the reference needs >= 2 (BVH.compute:101)", ctx->n);
+    if (int r = bind_device(ctx)) return r;
+    return do_tree(ctx);
+}
+
+int usrt_construct_bvh(usrt_context* ctx) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_TREE)) return fail(ctx, USRT_ERR_STATE, "construct_bvh: tree not built (call usrt_construct_tree)");
+    if (int r = bind_device(ctx)) return r;
+    return do_bvh(ctx);
+}
+
+int usrt_rebuild(usrt_context* ctx) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_TRIS)) return fail(ctx, USRT_ERR_STATE, "rebuild: no triangles uploaded");
+    if (ctx->n < 2) return fail(ctx, USRT_ERR_ARG, "rebuild: trianglesCount=%u; the reference needs >= 2 (BVH.compute:101)", ctx->n);
+    if (int r = bind_device(ctx)) return r;
+    const bool t = ctx->timing;
+    ctx->ev_valid = false;
+    if (t) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (int r = do_morton(ctx)) return r;
+    if (t) CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (int r = do_sort(ctx)) return r;
+    if (t) CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (int r = do_distribute(ctx)) return r;
+    if (t) CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (int r = do_tree(ctx)) return r;
+    if (t) CU(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (int r = do_bvh(ctx)) return r;
+    if (t) CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->ev_valid = t;
+    return USRT_OK;
+}
+
+int usrt_enable_stage_timing(usrt_context* ctx, int enabled) {
+    NEED_CTX(ctx);
+    ctx->timing = enabled != 0;
+    return USRT_OK;
+}
+
+int usrt_last_rebuild_ms(usrt_context* ctx, float out_ms[6]) {
+    NEED_CTX(ctx);
+    if (!out_ms) return USRT_ERR_ARG;
+    if (!ctx->ev_valid) return fail(ctx, USRT_ERR_STATE, "last_rebuild_ms: no timed rebuild");
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, cudaEventSynchronize(ctx->ev[5]));
+    for (int i = 0; i < 5; ++i) CU(ctx, cudaEventElapsedTime(&out_ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    CU(ctx, cudaEventElapsedTime(&out_ms[5], ctx->ev[0], ctx->ev[5]));
+    return USRT_OK;
+}
+
+int usrt_set_trace_mode(usrt_context* ctx, int mode) {
+    NEED_CTX(ctx);
+    if (mode != 0 && mode != 1) return fail(ctx, USRT_ERR_ARG, "trace mode must be 0 (strict) or 1 (culled)");
+    ctx->trace_mode = mode;
+    return USRT_OK;
+}
+
+int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
+                       const float camera_to_world[16], int y0, int y1, usrt_raycast_result* host_out) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_BVH)) return fail(ctx, USRT_ERR_STATE, "trace: BVH not built");
+    if (width <= 0 || height <= 0 || !camera_to_world || y0 < 0 || y1 > height || y0 > y1)
+        return fail(ctx, USRT_ERR_ARG, "trace_primary: bad frame %dx%d rows [%d,%d)", width, height, y0, y1);
+    if (int r = bind_device(ctx)) return r;
+    const uint64_t count = (uint64_t)width * (uint64_t)height;
+    if (int r = ensure_hits(ctx, count)) return r;
+    ctx->hits_count = count;
+    PrimaryParams p;
+    p.width = width; p.height = height; p.near_plane = near_plane; p.tan_half_fov = tan_half_fov;
+    memcpy(p.m, camera_to_world, sizeof(p.m));
+    p.y0 = y0; p.y1 = y1;
+    TraceScene s{ctx->packed_nodes, ctx->packed_tris, ctx->bvh};
+    CU(ctx, launch_trace_primary(s, p, ctx->hits, ctx->trace_mode, ctx->stream));
+    ctx->launches += (y1 > y0) ? 1 : 0;
+    if (host_out && y1 > y0) {
+        const size_t off = (size_t)y0 * width;
+        CU(ctx, cudaMemcpyAsync(host_out + off, ctx->hits + off, (size_t)(y1 - y0) * width * sizeof(usrt_raycast_result),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return USRT_OK;
+}
+
+int usrt_trace_rays_device(usrt_context* ctx, const void* dev_rays, uint64_t num_rays, void* dev_out) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_BVH)) return fail(ctx, USRT_ERR_STATE, "trace: BVH not built");
+    if (num_rays && !dev_rays) return fail(ctx, USRT_ERR_ARG, "trace_rays: null rays");
+    if (int r = bind_device(ctx)) return r;
+    usrt_raycast_result* out = static_cast<usrt_raycast_result*>(dev_out);
+    if (!out) {
+        if (int r = ensure_hits(ctx, num_rays)) return r;
+        out = ctx->hits;
+        ctx->hits_count = num_rays;
+    }
+    TraceScene s{ctx->packed_nodes, ctx->packed_tris, ctx->bvh};
+    CU(ctx, launch_trace_rays(s, static_cast<const float4*>(dev_rays), num_rays, out, ctx->trace_mode, ctx->stream));
+    ctx->launches += num_rays ? 1 : 0;
+    return USRT_OK;
+}
+
+int usrt_trace_rays(usrt_context* ctx, const float* host_rays, uint64_t num_rays, usrt_raycast_result* host_out) {
+    NEED_CTX(ctx);
+    if (num_rays == 0) return USRT_OK;
+    if (!host_rays) return fail(ctx, USRT_ERR_ARG, "trace_rays: null rays");
+    if (!(ctx->stage & ST_BVH)) return fail(ctx, USRT_ERR_STATE, "trace: BVH not built");
+    if (int r = bind_device(ctx)) return r;
+    if (int r = ensure_rays(ctx, num_rays)) return r;
+    CU(ctx, cudaMemcpyAsync(ctx->rays, host_rays, num_rays * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (int r = usrt_trace_rays_device(ctx, ctx->rays, num_rays, nullptr)) return r;
+    if (host_out) {
+        CU(ctx, cudaMemcpyAsync(host_out, ctx->hits, num_rays * sizeof(usrt_raycast_result), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return USRT_OK;
+}
+
+int usrt_hits_device(usrt_context* ctx, void** dev_ptr, uint64_t* count) {
+    NEED_CTX(ctx);
+    if (dev_ptr) *dev_ptr = ctx->hits;
+    if (count) *count = ctx->hits_count;
+    return USRT_OK;
+}
+
+static int buffer_info(usrt_context* ctx, int buffer, void** ptr, size_t* elem) {
+    switch (buffer) {
+        case USRT_BUF_KEYS: *ptr = ctx->keys; *elem = 4; return USRT_OK;
+        case USRT_BUF_TRIANGLE_INDEX: *ptr = ctx->tri_index; *elem = 4; return USRT_OK;
+        case USRT_BUF_TRIANGLE_DATA: *ptr = ctx->triangles; *elem = sizeof(usrt_triangle); return USRT_OK;
+        case USRT_BUF_TRIANGLE_AABB: *ptr = ctx->tri_aabb; *elem = sizeof(usrt_aabb); return USRT_OK;
+        case USRT_BUF_BVH_DATA: *ptr = ctx->bvh; *elem = sizeof(usrt_aabb); return USRT_OK;
+        case USRT_BUF_LEAF_NODES: *ptr = ctx->leaf; *elem = sizeof(usrt_leaf_node); return USRT_OK;
+        case USRT_BUF_INTERNAL_NODES: *ptr = ctx->internal; *elem = sizeof(usrt_internal_node); return USRT_OK;
+        default: return fail(ctx, USRT_ERR_ARG, "unknown buffer id %d", buffer);
+    }
+}
+
+int usrt_download(usrt_context* ctx, int buffer, void* host_dst, uint64_t count) {
+    NEED_CTX(ctx);
+    void* p; size_t elem;
+    if (int r = buffer_info(ctx, buffer, &p, &elem)) return r;
+    if (!host_dst || count > ctx->capacity) return fail(ctx, USRT_ERR_ARG, "download: count=%llu capacity=%u", (unsigned long long)count, ctx->capacity);
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, cudaMemcpyAsync(host_dst, p, count * elem, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return USRT_OK;
+}
+
+int usrt_device_ptr(usrt_context* ctx, int buffer, void** dev_ptr) {
+    NEED_CTX(ctx);
+    if (!dev_ptr) return USRT_ERR_ARG;
+    size_t elem;
+    return buffer_info(ctx, buffer, dev_ptr, &elem);
+}
+
+int usrt_count_corrupted_nodes(usrt_context* ctx, uint32_t* leaf_corrupted, uint32_t* internal_corrupted) {
+    NEED_CTX(ctx);
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, launch_count_corrupted(ctx->leaf, ctx->internal, ctx->n, ctx->small, ctx->stream));
+    ctx->launches += 1;
+    uint32_t h[2] = {0, 0};
+    CU(ctx, cudaMemcpyAsync(h, ctx->small, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (leaf_corrupted) *leaf_corrupted = h[0];
+    if (internal_corrupted) *internal_corrupted = h[1];
+    return USRT_OK;
+}
+
+}  // extern "C"

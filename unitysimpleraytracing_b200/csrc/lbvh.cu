@@ -1,0 +1,334 @@
+// lbvh.cu -- K3 DistributeKeys, K4 TreeConstructor, K5 BVHConstructor (+ packed traversal arrays).
+//
+// K3 replaces the serial CPU loop of Assets/_Scripts/MeshBufferContainer.cs:154-169 (and its full
+//    GPU->CPU->GPU round trip) with one single-pass scan kernel (decoupled look-back).
+// K4 replaces kernel TreeConstructor, Assets/_Shaders/BVH/BVH.compute:94-149 (delta :23-33,
+//    DetermineRange :35-52, FindSplit :54-92).
+// K5 replaces kernel BVHConstructor, BVH.compute:172-220 (MergeAABB :152-170).
+
+#include "usrt_internal.cuh"
+
+namespace usrt {
+
+namespace {
+
+// =================================================================================================
+// K3 -- new[0] = 0; new[i] = new[i-1] + max(k[i] - k[i-1], 1), wrapping uint32  (inclusive scan)
+// =================================================================================================
+constexpr int kScanBlock = 256;
+constexpr int kScanVecPerThread = 4;                                   // 4 x uint4 = 16 keys per thread
+constexpr int kScanTile = kScanBlock * kScanVecPerThread * 4;          // 4096 keys per tile
+constexpr uint64_t kScanAggregate = 1ull << 32, kScanPrefix = 2ull << 32, kScanFlagMask = 3ull << 32;
+
+// Each warp owns 512 consecutive keys as 4 rounds of one uint4 per lane (128-bit coalesced loads);
+// within a round a lane holds 4 consecutive keys, lanes are consecutive, rounds are consecutive.
+__global__ void __launch_bounds__(kScanBlock) k_distribute_keys(const uint32_t* __restrict__ src,
+                                                                uint32_t* __restrict__ dst, uint32_t n,
+                                                                uint64_t* __restrict__ status /* [0]=tile counter, [1+tile] */) {
+    __shared__ uint32_t s_warp_total[kScanBlock / 32];
+    __shared__ uint32_t s_tile_id;
+    __shared__ uint32_t s_tile_prefix;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile_id = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(status), 1ull);
+    __syncthreads();
+    const uint32_t tile = s_tile_id;
+    const uint32_t tile_base = tile * (uint32_t)kScanTile;
+    const uint32_t warp_base = tile_base + warp * (32u * 4u * kScanVecPerThread);
+
+    uint32_t k[kScanVecPerThread][4];
+    uint32_t prev[kScanVecPerThread];
+#pragma unroll
+    for (int r = 0; r < kScanVecPerThread; ++r) {
+        const uint32_t i0 = warp_base + (uint32_t)r * 128u + lane * 4u;
+        if (i0 + 3 < n) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + i0));
+            k[r][0] = q.x; k[r][1] = q.y; k[r][2] = q.z; k[r][3] = q.w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) k[r][c] = (i0 + c < n) ? __ldg(src + i0 + c) : 0u;
+        }
+        // key just before this lane's first key: previous lane's last, or one scalar load for lane 0
+        uint32_t p = __shfl_up_sync(0xFFFFFFFFu, k[r][3], 1);
+        if (lane == 0) p = (i0 > 0 && i0 < n) ? __ldg(src + i0 - 1) : 0u;
+        prev[r] = p;
+    }
+
+    // per-element increments d[i] = max(k[i]-k[i-1], 1) (d[0] = 0, d[i>=n] = 0), local inclusive sums
+    uint32_t carry = 0;                 // running total of this warp's earlier rounds
+    uint32_t x[kScanVecPerThread][4];
+#pragma unroll
+    for (int r = 0; r < kScanVecPerThread; ++r) {
+        const uint32_t i0 = warp_base + (uint32_t)r * 128u + lane * 4u;
+        uint32_t before = prev[r], run = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t i = i0 + c;
+            uint32_t d = k[r][c] - before;                 // wrapping, like C# unchecked uint
+            d = d > 1u ? d : 1u;                           // Math.Max(uint, 1)
+            if (i == 0 || i >= n) d = 0;
+            before = k[r][c];
+            run += d;
+            x[r][c] = run;
+        }
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += y;
+        }
+        const uint32_t excl = incl - run + carry;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[r][c] += excl;
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) s_warp_total[warp] = carry;
+    __syncthreads();
+
+    uint32_t warp_excl = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kScanBlock / 32; ++w) {
+        const uint32_t t = s_warp_total[w];
+        if (w < (int)warp) warp_excl += t;
+        tile_total += t;
+    }
+
+    // decoupled look-back on one 64-bit word per tile: flag << 32 | running sum
+    if (tid == 0) {
+        uint64_t* my = status + 1 + tile;
+        st_relaxed_u64(my, (tile == 0 ? kScanPrefix : kScanAggregate) | tile_total);
+        uint32_t exclusive = 0;
+        if (tile > 0) {
+            const uint64_t* look = my - 1;
+            while (true) {
+                uint64_t s;
+                do { s = ld_relaxed_u64(look); } while ((s & kScanFlagMask) == 0);
+                exclusive += (uint32_t)s;
+                if (s & kScanPrefix) break;
+                --look;
+            }
+            st_relaxed_u64(my, kScanPrefix | (uint32_t)(exclusive + tile_total));
+        }
+        s_tile_prefix = exclusive;
+    }
+    __syncthreads();
+    const uint32_t add = s_tile_prefix + warp_excl;
+
+#pragma unroll
+    for (int r = 0; r < kScanVecPerThread; ++r) {
+        const uint32_t i0 = warp_base + (uint32_t)r * 128u + lane * 4u;
+        if (i0 + 3 < n) {
+            *reinterpret_cast<uint4*>(dst + i0) = make_uint4(x[r][0] + add, x[r][1] + add, x[r][2] + add, x[r][3] + add);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (i0 + c < n) dst[i0 + c] = x[r][c] + add;
+        }
+    }
+}
+
+// =================================================================================================
+// K4 -- Karras LBVH topology, one thread per internal node
+// =================================================================================================
+struct KeyView {
+    const uint32_t* __restrict__ codes;
+    int n;
+    // BVH.compute:23-33. clz32 (:18-21) == __clz for the non-zero XOR DistributeKeys guarantees; 32 for 0.
+    __device__ __forceinline__ int delta(int x, int y) const {
+        if (x >= 0 && x <= n - 1 && y >= 0 && y <= n - 1) return __clz((int)(__ldg(codes + x) ^ __ldg(codes + y)));
+        return -1;
+    }
+};
+
+__global__ void __launch_bounds__(256) k_construct_tree(const uint32_t* __restrict__ codes, uint32_t n,
+                                                        usrt_internal_node* __restrict__ internal,
+                                                        usrt_leaf_node* __restrict__ leaf) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;                                            // BVH.compute:101
+    const KeyView kv{codes, (int)n};
+    const int idx = (int)i;
+
+    // DetermineRange (BVH.compute:35-52); uint*int products wrap in 32 bits as in HLSL
+    const int dl = kv.delta(idx, idx + 1) - kv.delta(idx, idx - 1);
+    const int d = (dl > 0) - (dl < 0);
+    const int dmin = kv.delta(idx, idx - d);
+    uint32_t lmax = 2;
+    while (kv.delta(idx, (int)((uint32_t)idx + lmax * (uint32_t)d)) > dmin) lmax *= 2;
+    int l = 0;
+    for (uint32_t t = lmax / 2; t >= 1; t /= 2)
+        if (kv.delta(idx, (int)((uint32_t)idx + ((uint32_t)l + t) * (uint32_t)d)) > dmin) l += (int)t;
+    const int j = idx + l * d;
+    const int first = min(idx, j), last = max(idx, j);
+
+    // FindSplit (BVH.compute:54-92)
+    int split;
+    {
+        const uint32_t first_code = __ldg(codes + first), last_code = __ldg(codes + last);
+        if (first_code == last_code) {
+            split = (first + last) >> 1;
+        } else {
+            const int common = __clz((int)(first_code ^ last_code));
+            split = first;
+            int step = last - first;
+            do {
+                step = (step + 1) >> 1;
+                const int cand = split + step;
+                if (cand < last) {
+                    const uint32_t c = __ldg(codes + cand);
+                    const uint32_t x = first_code ^ c;
+                    const int prefix = x ? __clz((int)x) : 32;
+                    if (prefix > common) split = cand;
+                }
+            } while (step > 1);
+        }
+    }
+
+    // BVH.compute:111-147. Node i's own five words are two 8-byte stores + index; `parent` belongs
+    // to the parent's thread. The root's parent keeps the NullLeaf sentinel (never written, :115).
+    const uint32_t left = (uint32_t)split, right = (uint32_t)split + 1;
+    const bool left_leaf = split == first, right_leaf = split + 1 == last;
+    uint32_t* node = reinterpret_cast<uint32_t*>(internal + i);
+    *reinterpret_cast<uint2*>(node + 0) = make_uint2(left, left_leaf ? USRT_LEAF_NODE : USRT_INTERNAL_NODE);
+    *reinterpret_cast<uint2*>(node + 2) = make_uint2(right, right_leaf ? USRT_LEAF_NODE : USRT_INTERNAL_NODE);
+    node[5] = i;
+    if (left_leaf) *reinterpret_cast<uint2*>(leaf + left) = make_uint2(i, left);
+    else internal[left].parent = i;
+    if (right_leaf) *reinterpret_cast<uint2*>(leaf + right) = make_uint2(i, right);
+    else internal[right].parent = i;
+}
+
+// =================================================================================================
+// K5 -- bottom-up AABB propagation, one thread per leaf
+// =================================================================================================
+__device__ __forceinline__ float sel_min(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float sel_max(float a, float b) { return a > b ? a : b; }
+
+__global__ void __launch_bounds__(256) k_construct_bvh(uint32_t n, const uint32_t* __restrict__ sorted_indices,
+                                                       const float4* __restrict__ tri_aabb,
+                                                       const float4* __restrict__ tris,
+                                                       const usrt_internal_node* __restrict__ internal,
+                                                       const usrt_leaf_node* __restrict__ leaf,
+                                                       float4* bvh, uint32_t* counters, float4* packed_nodes,
+                                                       float4* __restrict__ packed_tris) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;                                                // BVH.compute:179
+
+    const uint32_t tri = __ldg(sorted_indices + j);
+    float4 bmin = __ldg(tri_aabb + (size_t)tri * 2), bmax = __ldg(tri_aabb + (size_t)tri * 2 + 1);
+
+    // traversal-side copy of the vertices in leaf order (triangle id rides in a.w)
+    {
+        const float4* t = tris + (size_t)tri * 8;
+        float4 a = __ldg(t + 0), b = __ldg(t + 1), c = __ldg(t + 2);
+        a.w = __uint_as_float(tri); b.w = 0.0f; c.w = 0.0f;
+        packed_tris[(size_t)j * 3 + 0] = a;
+        packed_tris[(size_t)j * 3 + 1] = b;
+        packed_tris[(size_t)j * 3 + 2] = c;
+    }
+
+    uint32_t cur = j, cur_ref = 0x80000000u | j;                       // ref: leaf => bit 31 | sorted position
+    bool cur_is_leaf = true;
+    uint32_t parent = __ldg(&leaf[j].parent);                          // BVH.compute:181
+    while (parent != USRT_NULL) {                                      // :182
+        // :184-189 -- first arrival leaves, second arrival merges. XOR instead of CAS(0->1): same
+        // first/second decision, and the counter is back to 0 afterwards (re-runnable; the reference
+        // zeroes it only once, BVHConstructor.cs:41).
+        __threadfence();                                               // publish our box before the counter RMW
+        const uint32_t old = atomicXor(counters + parent, 1u);
+        if (old == 0) break;
+        __threadfence();
+
+        const uint32_t* node = reinterpret_cast<const uint32_t*>(internal + parent);
+        const uint2 l = __ldg(reinterpret_cast<const uint2*>(node + 0));   // leftNode, leftNodeType
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(node + 2));   // rightNode, rightNodeType
+        const uint32_t grand = __ldg(node + 4);
+        const bool i_am_left = (l.x == cur) && ((l.y == USRT_LEAF_NODE) == cur_is_leaf);
+        const uint2 sib = i_am_left ? r : l;
+
+        // sibling box: written by another thread of this launch => read through L2 (.cg), never L1
+        float4 smin, smax;
+        uint32_t sib_ref;
+        if (sib.y == USRT_INTERNAL_NODE) {                             // :197-213
+            smin = __ldcg(bvh + (size_t)sib.x * 2);
+            smax = __ldcg(bvh + (size_t)sib.x * 2 + 1);
+            sib_ref = sib.x;
+        } else {
+            const uint32_t stri = __ldg(sorted_indices + sib.x);
+            smin = __ldg(tri_aabb + (size_t)stri * 2);
+            smax = __ldg(tri_aabb + (size_t)stri * 2 + 1);
+            sib_ref = 0x80000000u | sib.x;
+        }
+        const float4 lmin = i_am_left ? bmin : smin, lmax = i_am_left ? bmax : smax;
+        const float4 rmin = i_am_left ? smin : bmin, rmax = i_am_left ? smax : bmax;
+        const uint32_t lref = i_am_left ? cur_ref : sib_ref, rref = i_am_left ? sib_ref : cur_ref;
+
+        // MergeAABB (:152-170), pads = 0
+        bmin = make_float4(sel_min(lmin.x, rmin.x), sel_min(lmin.y, rmin.y), sel_min(lmin.z, rmin.z), 0.0f);
+        bmax = make_float4(sel_max(lmax.x, rmax.x), sel_max(lmax.y, rmax.y), sel_max(lmax.z, rmax.z), 0.0f);
+        __stcg(bvh + (size_t)parent * 2, bmin);                        // :215
+        __stcg(bvh + (size_t)parent * 2 + 1, bmax);
+
+        // packed traversal node: both child boxes + child refs in one 64-byte record
+        float4* pn = packed_nodes + (size_t)parent * 4;
+        pn[0] = make_float4(lmin.x, lmin.y, lmin.z, lmax.x);
+        pn[1] = make_float4(lmax.y, lmax.z, rmin.x, rmin.y);
+        pn[2] = make_float4(rmin.z, rmax.x, rmax.y, rmax.z);
+        pn[3] = make_float4(__uint_as_float(lref), __uint_as_float(rref), 0.0f, 0.0f);
+
+        cur = parent; cur_ref = parent; cur_is_leaf = false;
+        parent = grand;                                                // :217
+    }
+}
+
+__global__ void k_count_corrupted(const usrt_leaf_node* __restrict__ leaf, const usrt_internal_node* __restrict__ internal,
+                                  uint32_t n, uint32_t* __restrict__ out2) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // MeshBufferContainer.cs:181-195
+    if (i < n && leaf[i].index == USRT_NULL && leaf[i].parent == USRT_NULL) atomicAdd(out2 + 0, 1u);
+    if (i + 1 < n && internal[i].index == USRT_NULL && internal[i].parent == USRT_NULL) atomicAdd(out2 + 1, 1u);
+}
+
+}  // namespace
+
+uint64_t distribute_status_bytes(uint32_t n) {
+    const uint64_t tiles = ((uint64_t)n + kScanTile - 1) / kScanTile;
+    return (tiles + 1) * 8;
+}
+
+cudaError_t launch_distribute_keys(const uint32_t* src, uint32_t* dst, uint32_t n, void* scan_status,
+                                   cudaStream_t stream, int* launches) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(scan_status, 0, distribute_status_bytes(n), stream);
+    if (e != cudaSuccess) return e;
+    const uint32_t tiles = (uint32_t)(((uint64_t)n + kScanTile - 1) / kScanTile);
+    k_distribute_keys<<<tiles, kScanBlock, 0, stream>>>(src, dst, n, static_cast<uint64_t*>(scan_status));
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_construct_tree(const uint32_t* keys, uint32_t n, usrt_internal_node* internal,
+                                  usrt_leaf_node* leaf, cudaStream_t stream) {
+    const uint32_t threads = n - 1;
+    k_construct_tree<<<(threads + 255) / 256, 256, 0, stream>>>(keys, n, internal, leaf);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
+                                 const usrt_triangle* tris, const usrt_internal_node* internal,
+                                 const usrt_leaf_node* leaf, usrt_aabb* bvh, uint32_t* counters, float4* packed_nodes,
+                                 float4* packed_tris, cudaStream_t stream) {
+    k_construct_bvh<<<(n + 255) / 256, 256, 0, stream>>>(n, sorted_indices, reinterpret_cast<const float4*>(tri_aabb),
+                                                         reinterpret_cast<const float4*>(tris), internal, leaf,
+                                                         reinterpret_cast<float4*>(bvh), counters, packed_nodes,
+                                                         packed_tris);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count_corrupted(const usrt_leaf_node* leaf, const usrt_internal_node* internal, uint32_t n,
+                                   uint32_t* out2, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(out2, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    k_count_corrupted<<<(n + 255) / 256, 256, 0, stream>>>(leaf, internal, n, out2);
+    return cudaGetLastError();
+}
+
+}  // namespace usrt

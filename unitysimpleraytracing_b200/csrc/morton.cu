@@ -1,0 +1,73 @@
+// morton.cu -- K1: per-triangle padded AABB, centroid and 30-bit Morton code.
+//
+// Replaces the CPU loop of Assets/_Scripts/MeshBufferContainer.cs:123-146 (GetCentroidAndAABB :52-71,
+// NormalizeCentroid :73-83, Morton3D :41-50, ExpandBits :32-39). One thread per triangle.
+// HBM-bound: 48 B read (three 16-B vertex slots of the 128-B Triangle) + 32 B AABB + 4 B key + 4 B
+// value = 88 algorithmic bytes per triangle. All fp32 arithmetic is spelled with round-to-nearest
+// intrinsics (no FMA contraction, IEEE division) so the keys are bit-identical to the oracle.
+
+#include "usrt_internal.cuh"
+
+namespace usrt {
+
+__device__ __forceinline__ uint32_t expand_bits(uint32_t v) {   // MeshBufferContainer.cs:32-39
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__device__ __forceinline__ float sel_min(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float sel_max(float a, float b) { return a > b ? a : b; }
+
+__device__ __forceinline__ uint32_t quantise(float x) {          // MeshBufferContainer.cs:43,46
+    x = sel_min(sel_max(__fmul_rn(x, 1024.0f), 0.0f), 1023.0f);
+    return (uint32_t)x;                                           // truncation, like C# (uint)float
+}
+
+__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ tris, uint32_t n, float whole_min,
+                                                float whole_max, uint32_t* __restrict__ keys,
+                                                uint32_t* __restrict__ values, float4* __restrict__ aabbs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* t = tris + (size_t)i * 8;       // 128-B Triangle = 8 x float4; a, b, c are slots 0..2
+    const float4 a = __ldg(t + 0), b = __ldg(t + 1), c = __ldg(t + 2);
+
+    // GetCentroidAndAABB (:52-71)
+    const float mnx = __fsub_rn(sel_min(sel_min(a.x, b.x), c.x), 0.001f);
+    const float mny = __fsub_rn(sel_min(sel_min(a.y, b.y), c.y), 0.001f);
+    const float mnz = __fsub_rn(sel_min(sel_min(a.z, b.z), c.z), 0.001f);
+    const float mxx = __fadd_rn(sel_max(sel_max(a.x, b.x), c.x), 0.001f);
+    const float mxy = __fadd_rn(sel_max(sel_max(a.y, b.y), c.y), 0.001f);
+    const float mxz = __fadd_rn(sel_max(sel_max(a.z, b.z), c.z), 0.001f);
+    float cx = __fmul_rn(__fadd_rn(mnx, mxx), 0.5f);
+    float cy = __fmul_rn(__fadd_rn(mny, mxy), 0.5f);
+    float cz = __fmul_rn(__fadd_rn(mnz, mxz), 0.5f);
+
+    // NormalizeCentroid (:73-83): subtract, then a true division by (max - min)
+    const float extent = __fsub_rn(whole_max, whole_min);
+    cx = __fdiv_rn(__fsub_rn(cx, whole_min), extent);
+    cy = __fdiv_rn(__fsub_rn(cy, whole_min), extent);
+    cz = __fdiv_rn(__fsub_rn(cz, whole_min), extent);
+
+    // Morton3D (:41-50)
+    const uint32_t key = expand_bits(quantise(cx)) * 4 + expand_bits(quantise(cy)) * 2 + expand_bits(quantise(cz));
+
+    keys[i] = key;
+    values[i] = i;                                                 // :132
+    aabbs[(size_t)i * 2 + 0] = make_float4(mnx, mny, mnz, 0.0f);   // pads are C# default(0)
+    aabbs[(size_t)i * 2 + 1] = make_float4(mxx, mxy, mxz, 0.0f);
+}
+
+cudaError_t launch_morton(const usrt_triangle* tris, uint32_t n, float whole_min, float whole_max, uint32_t* keys,
+                          uint32_t* values, usrt_aabb* aabbs, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t block = 256;
+    const uint32_t grid = (n + block - 1) / block;
+    k_morton<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(tris), n, whole_min, whole_max, keys, values,
+                                         reinterpret_cast<float4*>(aabbs));
+    return cudaGetLastError();
+}
+
+}  // namespace usrt

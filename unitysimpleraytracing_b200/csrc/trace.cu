@@ -1,0 +1,213 @@
+// trace.cu -- K6: stack-based BVH traversal with the reference's slab and Moller-Trumbore tests.
+//
+// Replaces kernel Raytracing, Assets/_Shaders/Raytracing/Raytracing.compute:105-176 (ray generation
+// :108-126, RayBoxIntersection :75-87, RayTriangleIntersection :37-73, CheckTriangle :89-103), up to
+// and excluding the shading epilogue (:178-184). Output is the RaycastResult hit record (:30-35).
+//
+// Visiting semantics are the reference's exactly (strict mode): DFS from node 0, left child then
+// right child handled at the parent's visit (leaf => tested now, internal => pushed), so the right
+// internal subtree is walked before the left one; a candidate replaces the best hit only if strictly
+// closer; no distance culling, no t > 0 test. The reference tests a node's box when it is POPPED;
+// here the parent's 64-byte packed record carries both child boxes, so a child is tested before it
+// is PUSHED -- the same boxes are tested against the same ray and the surviving visit order is
+// identical, but each visit costs one 64-byte record instead of a 32-byte box + 24-byte node +
+// 8-byte leaf + 4-byte index chase. Leaf boxes are the triangles' own padded AABBs, i.e. the
+// CheckTriangle box test (:91).
+//
+// fp32 arithmetic is written with round-to-nearest intrinsics in the oracle's canonical order
+// (SURVEY.md 8a): no FMA contraction, IEEE division and square root.
+
+#include "usrt_internal.cuh"
+
+namespace usrt {
+
+namespace {
+
+struct Ray { float ox, oy, oz, dx, dy, dz, ix, iy, iz; };
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return add(add(mul(ax, bx), mul(ay, by)), mul(az, bz));
+}
+
+// Constants.cginc:7 -- integer literal 0x7F7FFFFF converted to float
+__device__ __forceinline__ float max_float() { return __uint_as_float(0x4EFF0000u); }
+
+// Raytracing.compute:75-87; returns tmin through *entry for the (non-parity) culled mode
+__device__ __forceinline__ bool ray_box(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
+                                        const Ray& r, float* entry) {
+    const float t1x = mul(sub(bminx, r.ox), r.ix), t2x = mul(sub(bmaxx, r.ox), r.ix);
+    const float t1y = mul(sub(bminy, r.oy), r.iy), t2y = mul(sub(bmaxy, r.oy), r.iy);
+    const float t1z = mul(sub(bminz, r.oz), r.iz), t2z = mul(sub(bmaxz, r.oz), r.iz);
+    const float tmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+    const float tmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+    *entry = tmin;
+    return tmax > tmin && tmax > 0.0f;
+}
+
+// Raytracing.compute:37-73 + the strict '<' replace of CheckTriangle :95-99
+__device__ __forceinline__ void ray_triangle(const Ray& r, const float4 v0, const float4 v1, const float4 v2,
+                                             usrt_raycast_result& best) {
+    const float e1x = sub(v1.x, v0.x), e1y = sub(v1.y, v0.y), e1z = sub(v1.z, v0.z);
+    const float e2x = sub(v2.x, v0.x), e2y = sub(v2.y, v0.y), e2z = sub(v2.z, v0.z);
+    // pvec = cross(dir, e2)
+    const float px = sub(mul(r.dy, e2z), mul(r.dz, e2y));
+    const float py = sub(mul(r.dz, e2x), mul(r.dx, e2z));
+    const float pz = sub(mul(r.dx, e2y), mul(r.dy, e2x));
+    const float det = dot3(e1x, e1y, e1z, px, py, pz);
+    if (det < 1e-8f && det > -1e-8f) return;
+    const float inv_det = __fdiv_rn(1.0f, det);
+    const float tx = sub(r.ox, v0.x), ty = sub(r.oy, v0.y), tz = sub(r.oz, v0.z);
+    const float u = mul(dot3(tx, ty, tz, px, py, pz), inv_det);
+    if (u < 0.0f || u > 1.0f) return;
+    // qvec = cross(tvec, e1)
+    const float qx = sub(mul(ty, e1z), mul(tz, e1y));
+    const float qy = sub(mul(tz, e1x), mul(tx, e1z));
+    const float qz = sub(mul(tx, e1y), mul(ty, e1x));
+    const float v = mul(dot3(r.dx, r.dy, r.dz, qx, qy, qz), inv_det);
+    if (v < 0.0f || add(u, v) > 1.0f) return;
+    const float dist = mul(dot3(e2x, e2y, e2z, qx, qy, qz), inv_det);
+    if (dist < best.distance) {
+        best.distance = dist;
+        best.triangleIndex = __float_as_uint(v0.w);
+        best.uv[0] = u;
+        best.uv[1] = v;
+    }
+}
+
+template <bool kCulled>
+__device__ __forceinline__ usrt_raycast_result traverse(const TraceScene& s, const Ray& ray) {
+    usrt_raycast_result best;
+    best.distance = max_float();                       // Raytracing.compute:129-131
+    best.triangleIndex = 0;
+    best.uv[0] = 0.0f; best.uv[1] = 0.0f;
+
+    // node 0 is popped and its own box tested first (:135-146)
+    {
+        const float4 rmin = __ldg(reinterpret_cast<const float4*>(s.bvh));
+        const float4 rmax = __ldg(reinterpret_cast<const float4*>(s.bvh) + 1);
+        float entry;
+        if (!ray_box(rmin.x, rmin.y, rmin.z, rmax.x, rmax.y, rmax.z, ray, &entry)) return best;
+    }
+
+    uint32_t stack[64];                                // :133
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp != 0) {
+        const uint32_t index = stack[--sp];
+        const float4* pn = s.packed_nodes + (size_t)index * 4;
+        const float4 q0 = __ldg(pn + 0), q1 = __ldg(pn + 1), q2 = __ldg(pn + 2), q3 = __ldg(pn + 3);
+        const uint32_t lref = __float_as_uint(q3.x), rref = __float_as_uint(q3.y);
+
+        float lentry, rentry;
+        bool lhit = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ray, &lentry);
+        bool rhit = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ray, &rentry);
+        if (kCulled) {
+            lhit = lhit && !(lentry > best.distance);
+        }
+        // left child (:148-160)
+        if (lhit) {
+            if (lref & 0x80000000u) {
+                const float4* t = s.packed_tris + (size_t)(lref & 0x7FFFFFFFu) * 3;
+                ray_triangle(ray, __ldg(t + 0), __ldg(t + 1), __ldg(t + 2), best);
+            } else {
+                stack[sp++] = lref;
+            }
+        }
+        if (kCulled) {
+            rhit = rhit && !(rentry > best.distance);
+        }
+        // right child (:162-175)
+        if (rhit) {
+            if (rref & 0x80000000u) {
+                const float4* t = s.packed_tris + (size_t)(rref & 0x7FFFFFFFu) * 3;
+                ray_triangle(ray, __ldg(t + 0), __ldg(t + 1), __ldg(t + 2), best);
+            } else {
+                stack[sp++] = rref;
+            }
+        }
+    }
+    return best;
+}
+
+// Raytracing.compute:108-126 with the uniforms of RaytracingMeshDrawer.cs:78-81
+__device__ __forceinline__ Ray primary_ray(const PrimaryParams& p, uint32_t x, uint32_t y) {
+    const float near_plane = p.near_plane;
+    const float fov = p.tan_half_fov;
+    const float height = mul(mul(2.0f, near_plane), fov);
+    const float fw = __int2float_rn(p.width), fh = __int2float_rn(p.height);
+    const float width = __fdiv_rn(mul(fw, height), fh);
+    const float dx = add(__fdiv_rn(-width, 2.0f), mul(__fdiv_rn(width, fw), add(__uint2float_rn(x), 0.5f)));
+    const float dy = add(__fdiv_rn(-height, 2.0f), mul(__fdiv_rn(height, fh), add(__uint2float_rn(y), 0.5f)));
+    const float dz = -near_plane;
+    const float* m = p.m;
+    Ray r;
+    // origin = mul(M, (0,0,0,1)), dir = mul(M, (dir,0)): row . vector, left to right, w term included
+    r.ox = add(add(add(mul(m[0], 0.0f), mul(m[1], 0.0f)), mul(m[2], 0.0f)), mul(m[3], 1.0f));
+    r.oy = add(add(add(mul(m[4], 0.0f), mul(m[5], 0.0f)), mul(m[6], 0.0f)), mul(m[7], 1.0f));
+    r.oz = add(add(add(mul(m[8], 0.0f), mul(m[9], 0.0f)), mul(m[10], 0.0f)), mul(m[11], 1.0f));
+    const float wx = add(add(add(mul(m[0], dx), mul(m[1], dy)), mul(m[2], dz)), mul(m[3], 0.0f));
+    const float wy = add(add(add(mul(m[4], dx), mul(m[5], dy)), mul(m[6], dz)), mul(m[7], 0.0f));
+    const float wz = add(add(add(mul(m[8], dx), mul(m[9], dy)), mul(m[10], dz)), mul(m[11], 0.0f));
+    const float len = __fsqrt_rn(dot3(wx, wy, wz, wx, wy, wz));
+    r.dx = __fdiv_rn(wx, len); r.dy = __fdiv_rn(wy, len); r.dz = __fdiv_rn(wz, len);
+    r.ix = __fdiv_rn(1.0f, r.dx); r.iy = __fdiv_rn(1.0f, r.dy); r.iz = __fdiv_rn(1.0f, r.dz);
+    return r;
+}
+
+__device__ __forceinline__ void store_hit(usrt_raycast_result* out, size_t i, const usrt_raycast_result& h) {
+    reinterpret_cast<float4*>(out)[i] = make_float4(h.distance, __uint_as_float(h.triangleIndex), h.uv[0], h.uv[1]);
+}
+
+// One warp = an 8 x 4 pixel tile, one CTA = 4 warps = 16 x 8 pixels. Only on-screen pixels are traced
+// (the reference dispatches (W/32+1) x (H/32+1) groups with no bounds guard, RaytracingMeshDrawer.cs:83).
+constexpr int kTileW = 16, kTileH = 8;
+
+template <bool kCulled>
+__global__ void __launch_bounds__(128) k_trace_primary(TraceScene scene, PrimaryParams p, usrt_raycast_result* __restrict__ out) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t x = blockIdx.x * kTileW + (warp & 1u) * 8u + (lane & 7u);
+    const uint32_t y = (uint32_t)p.y0 + blockIdx.y * kTileH + (warp >> 1) * 4u + (lane >> 3);
+    if (x >= (uint32_t)p.width || y >= (uint32_t)p.y1) return;
+    const Ray ray = primary_ray(p, x, y);
+    const usrt_raycast_result h = traverse<kCulled>(scene, ray);
+    store_hit(out, (size_t)y * (size_t)p.width + x, h);                // hit record index = y*W + x
+}
+
+template <bool kCulled>
+__global__ void __launch_bounds__(128) k_trace_rays(TraceScene scene, const float4* __restrict__ rays, uint64_t num_rays,
+                                                    usrt_raycast_result* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_rays) return;
+    const float4 o = __ldg(rays + i * 2), d = __ldg(rays + i * 2 + 1);
+    Ray r;
+    r.ox = o.x; r.oy = o.y; r.oz = o.z;
+    r.dx = d.x; r.dy = d.y; r.dz = d.z;
+    r.ix = __fdiv_rn(1.0f, d.x); r.iy = __fdiv_rn(1.0f, d.y); r.iz = __fdiv_rn(1.0f, d.z);
+    const usrt_raycast_result h = traverse<kCulled>(scene, r);
+    store_hit(out, (size_t)i, h);
+}
+
+}  // namespace
+
+cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p, usrt_raycast_result* out, int mode,
+                                 cudaStream_t stream) {
+    if (p.y1 <= p.y0 || p.width <= 0) return cudaSuccess;
+    const dim3 grid((p.width + kTileW - 1) / kTileW, (p.y1 - p.y0 + kTileH - 1) / kTileH);
+    if (mode == 1) k_trace_primary<true><<<grid, 128, 0, stream>>>(scene, p, out);
+    else k_trace_primary<false><<<grid, 128, 0, stream>>>(scene, p, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_rays(const TraceScene& scene, const float4* rays, uint64_t num_rays, usrt_raycast_result* out,
+                              int mode, cudaStream_t stream) {
+    if (num_rays == 0) return cudaSuccess;
+    const uint32_t grid = (uint32_t)((num_rays + 127) / 128);
+    if (mode == 1) k_trace_rays<true><<<grid, 128, 0, stream>>>(scene, rays, num_rays, out);
+    else k_trace_rays<false><<<grid, 128, 0, stream>>>(scene, rays, num_rays, out);
+    return cudaGetLastError();
+}
+
+}  // namespace usrt

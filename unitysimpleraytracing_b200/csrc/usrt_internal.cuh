@@ -1,0 +1,105 @@
+// usrt_internal.cuh -- shared declarations of libusrt_b200.so (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/usrt.h"
+
+static_assert(sizeof(usrt_aabb) == 32, "AABB layout (Constants.cginc:9-15)");
+static_assert(sizeof(usrt_internal_node) == 24, "InternalNode layout (Constants.cginc:20-28)");
+static_assert(sizeof(usrt_leaf_node) == 8, "LeafNode layout (Constants.cginc:30-34)");
+static_assert(sizeof(usrt_triangle) == 128, "Triangle layout (Constants.cginc:36-54)");
+static_assert(sizeof(usrt_raycast_result) == 16, "RaycastResult layout (Raytracing.compute:30-35)");
+
+namespace usrt {
+
+constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
+constexpr int kRadixBits = 8;         // Constants.cginc:1  RADIX
+constexpr int kRadix = 256;           // Constants.cginc:2  BUCKET_SIZE
+constexpr int kSortPasses = 4;        // ComputeBufferSorter.cs:102  bitOffset = 0,8,16,24
+
+// ---- radix sort scratch (K2) ----------------------------------------------------------------
+struct SortScratch {
+    uint32_t* keys_alt = nullptr;      // ping-pong partners for the standalone sorter
+    uint32_t* vals_alt = nullptr;
+    uint64_t alt_capacity = 0;         // elements
+    uint32_t* hist = nullptr;          // [4][256] digit histograms, then exclusive digit bases
+    void* status = nullptr;            // [4 tile counters (as 64 x u32 header)] + [passes][tiles][256] look-back words
+    uint64_t status_bytes = 0;
+};
+
+// Launches enqueue on `stream`; every function returns the first CUDA error it saw.
+// K2: stable LSD sort of count pairs, result back in (keys, vals). alt buffers must hold count elements.
+cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt, uint64_t count,
+                       SortScratch& scratch, cudaStream_t stream, uint64_t* launches);
+// One stable partition pass src -> dst by digit (key >> bit_offset) & 255.
+cudaError_t partition_pass(const uint32_t* src_keys, const uint32_t* src_vals, uint32_t* dst_keys, uint32_t* dst_vals,
+                           uint64_t count, int bit_offset, uint32_t* histogram_out, SortScratch& scratch,
+                           cudaStream_t stream, uint64_t* launches);
+cudaError_t sort_scratch_reserve(SortScratch& scratch, uint64_t count, bool need_alt);
+void sort_scratch_free(SortScratch& scratch);
+
+// K1
+cudaError_t launch_morton(const usrt_triangle* tris, uint32_t n, float whole_min, float whole_max, uint32_t* keys,
+                          uint32_t* values, usrt_aabb* aabbs, cudaStream_t stream);
+// K3 (src != dst; dst receives the distributed keys). scan_status: >= (tiles+1) x 8 bytes, zeroed by the call.
+cudaError_t launch_distribute_keys(const uint32_t* src, uint32_t* dst, uint32_t n, void* scan_status,
+                                   cudaStream_t stream, int* launches);
+uint64_t distribute_status_bytes(uint32_t n);
+// K4
+cudaError_t launch_construct_tree(const uint32_t* keys, uint32_t n, usrt_internal_node* internal,
+                                  usrt_leaf_node* leaf, cudaStream_t stream);
+// K5 (+ packed traversal arrays)
+cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
+                                 const usrt_triangle* tris, const usrt_internal_node* internal,
+                                 const usrt_leaf_node* leaf, usrt_aabb* bvh, uint32_t* counters, float4* packed_nodes,
+                                 float4* packed_tris, cudaStream_t stream);
+// validator (MeshBufferContainer.cs:181-195)
+cudaError_t launch_count_corrupted(const usrt_leaf_node* leaf, const usrt_internal_node* internal, uint32_t n,
+                                   uint32_t* out2, cudaStream_t stream);
+
+// K6
+struct TraceScene {
+    const float4* packed_nodes;   // 4 x float4 per internal node (both child boxes + child refs)
+    const float4* packed_tris;    // 3 x float4 per leaf, in sorted (leaf) order; .w of the first = triangle id
+    const usrt_aabb* bvh;         // root box = bvh[0]
+};
+struct PrimaryParams {
+    int width, height;
+    float near_plane, tan_half_fov;
+    float m[16];                  // row-major cameraToWorld
+    int y0, y1;
+};
+cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p, usrt_raycast_result* out, int mode,
+                                 cudaStream_t stream);
+cudaError_t launch_trace_rays(const TraceScene& scene, const float4* rays, uint64_t num_rays, usrt_raycast_result* out,
+                              int mode, cudaStream_t stream);
+
+// ---- small device helpers -------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+#endif
+
+}  // namespace usrt
