@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LBVH build + ray-cast path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Workload (BASELINE.json configs[1]): 1,048,576-triangle scene (tessellated sphere + height field),
+one STEP = full rebuild (Morton -> radix sort -> DistributeKeys -> tree -> refit) followed by a
+1920x1080 primary-ray cast. Metric = Mrays/s = rays per step / device time per step.
+
+Prints ONE JSON line (rank 0). Extra keys beside the contract: `stages` (per-stage device ms of the
+same steps), `sort` (2^26-pair key/value sort leg), `roofline` (dominant HBM-bound kernel: one
+onesweep radix pass, timed live with CUDA events), `rooflines` (every build kernel), `cpu_baseline`.
+
+N > 1: rays are sharded (BASELINE configs[4] shape, north_star (a)): every rank holds a replica of
+the BVH (rebuilt each step, deterministic), traces its own 1080p sample of an N-spp frame, and the
+hit records are all-gathered over NCCL on a side stream, overlapped with the next step's compute.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+SORT_LOG2 = 26
+# algorithmic bytes per unit (DESIGN.md "Kernels and rooflines")
+BYTES = dict(morton=88, sort_pair=68, sort_pass_pair=16, distribute=8, tree=36,
+             bvh=140 + 64 + 96)   # reference refit 140 B/tri + packed node 64 B + packed triangle 48 B read + 48 B write
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            # under load = samples in the upper half of the observed range
+            hi = [x for x in sm if x >= 0.5 * max(sm)]
+            out.update(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def build_scene():
+    from unitysimpleraytracing_b200 import meshes
+    tris = meshes.scene_c2()
+    return tris, meshes.SCENE_C2_CAMERA
+
+
+def camera_for_rank(cam, rank):
+    """Rank r traces sample r of the frame: the same camera nudged by a sub-pixel offset in x/y."""
+    m = np.array(cam["cam_to_world"], np.float32).copy()
+    m[0, 3] += np.float32(0.0131 * rank)
+    m[1, 3] += np.float32(0.0071 * rank)
+    return m
+
+
+# =================================================================================================
+# reference arm: the reference's algorithm (oracle C++ twin) on the host cores
+# =================================================================================================
+def cpu_step(ref_mod, tris, cam, rows, threads):
+    """One bounded CPU sample of the step: full single-threaded rebuild (the reference's CPU stages are
+    serial loops) + `rows` rows of the 1080p frame traced on `threads` host threads, extrapolated."""
+    tm = {}
+    t0 = time.perf_counter()
+    scene = ref_mod.Scene(tris, timings=tm)
+    t_build = time.perf_counter() - t0
+    y0 = (H - rows) // 2
+    t1 = time.perf_counter()
+    scene.trace_primary(W, H, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], y0=y0, y1=y0 + rows, threads=threads)
+    t_trace_rows = time.perf_counter() - t1
+    t_frame = t_trace_rows * (H / rows)
+    return dict(step_s=t_build + t_frame, build_s=t_build, trace_rows_s=t_trace_rows, trace_frame_s=t_frame, stages=tm)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                     # rank 0 alone runs the CPU arm
+    from oracle import usrt_oracle as O
+    O.build()
+    tris, cam = build_scene()
+    threads = os.cpu_count() or 1
+    rows = 40
+    for _ in range(max(args.warmup, 0)):
+        cpu_step(O, tris, cam, 8, threads)
+    samples = [cpu_step(O, tris, cam, rows, threads) for _ in range(args.steps)]
+    step_s = statistics.mean(s["step_s"] for s in samples)
+    value = W * H / step_s / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s (1080p, 1M tris; step = full LBVH rebuild incl. sort + primary-ray cast)",
+        "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: 1,048,576-tri sphere+height-field, full rebuild + 1920x1080 primary rays",
+                   "triangles": int(len(tris)), "rays_per_step": W * H, "parallelism": "host threads"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                         "sample": "per step: full 1M-tri rebuild on 1 thread (%.0f ms) + %d of %d rows traced on %d threads, "
+                                   "frame time extrapolated by rows" % (statistics.mean(s["build_s"] for s in samples) * 1e3,
+                                                                        rows, H, threads)},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stages_ms": {"build": statistics.mean(s["build_s"] for s in samples) * 1e3,
+                      "trace_frame_extrapolated": statistics.mean(s["trace_frame_s"] for s in samples) * 1e3},
+        "note": "reference is GPU-only HLSL + Unity C#; this arm times its algorithm restated in C++ (oracle/), see DESIGN.md",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =================================================================================================
+# this repo's arm
+# =================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from unitysimpleraytracing_b200 import _lib, host
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peak_gbs, peak_src = measured_peaks()
+
+    tris, cam = build_scene()
+    n = len(tris)
+    rays = W * H
+    m = camera_for_rank(cam, rank)
+
+    ctx = host.Context(n, device=local_rank)
+    # one non-default torch stream carries everything: the library's kernels (usrt_set_stream) and the
+    # torch.cuda.Events that time them (torch events only see the stream they are recorded on)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+    ctx.upload_triangles(tris)
+    ctx.enable_stage_timing(True)
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    comm_stream = torch.cuda.Stream() if world > 1 else None
+    gathered = [torch.empty(world * rays * 4, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    hit_copy = [torch.empty(rays * 4, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+
+    def step(i, ev0=None, ev1=None):
+        flush.fill_(i & 0xFF)                                           # L2 flush, outside the event pair
+        if ev0 is not None:
+            ev0.record(stream)
+        ctx.rebuild()
+        ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=False)
+        if world > 1:
+            # hand the frame to the comm stream: copy out of the context's hit buffer, then all-gather
+            # there while the next step computes here
+            ptr, cnt = ctx.hits_device()
+            src = _as_tensor(torch, ptr, cnt * 4, dev)
+            buf = i & 1
+            stream.wait_stream(comm_stream)                             # buffer `buf` free again (2 steps ago)
+            hit_copy[buf].copy_(src, non_blocking=True)
+            comm_stream.wait_stream(stream)
+            with torch.cuda.stream(comm_stream):
+                dist.all_gather_into_tensor(gathered[buf], hit_copy[buf])
+        if ev1 is not None:
+            ev1.record(stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+
+    # ---- timed region -------------------------------------------------------------------------
+    launches0 = ctx.kernel_launches
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_acc = {}
+    sort_acc = {}
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i, *evs[i])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.kernel_launches - launches0
+    # per-stage device times (events recorded inside the library on the same stream), on extra
+    # steps of the same workload so that the queries' host syncs stay out of the timed region
+    for i in range(5):
+        step(i)
+        for k, v in ctx.last_rebuild_ms().items():
+            stage_acc.setdefault(k, []).append(v)
+        for k, v in ctx.last_sort_ms().items():
+            sort_acc.setdefault(k, []).append(v)
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = sum(step_ms)
+    if world > 1:
+        # the gathers overlap compute; what bounds the job is the slower of the two streams: use the
+        # wall time of the whole region (device-synchronised on both sides) minus nothing
+        total_ms = max(total_ms, t_wall * 1e3 - _flush_ms(torch, flush, stream) * args.steps)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * rays / (ms_per_step * 1e-3) / 1e6
+
+    stages = {k: statistics.mean(v) for k, v in stage_acc.items()}
+    stages["sort_kernels"] = {k: statistics.mean(v) for k, v in sort_acc.items()}
+    # trace-only time, measured directly
+    tr_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(i)
+        tr_ev[i][0].record(stream)
+        ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=False)
+        tr_ev[i][1].record(stream)
+    torch.cuda.synchronize()
+    trace_ms = statistics.mean(a.elapsed_time(b) for a, b in tr_ev)
+    stages["trace"] = trace_ms
+    clocks = sampler.stop() if sampler else None
+
+    line = None
+    if rank == 0:
+        # ---- e2e: the same step through the C ABI with HOST buffers -------------------------------
+        pinned_tris = torch.from_numpy(tris.view(np.uint8).reshape(-1)).pin_memory()
+        pinned_hits = torch.empty(rays * 16, dtype=torch.uint8).pin_memory()
+        tris_h = pinned_tris.numpy().view(tris.dtype)
+        hits_h = pinned_hits.numpy().view(np.dtype([("distance", "<f4"), ("triangleIndex", "<u4"), ("uv", "<f4", 2)]))
+        e2e_steps = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            ctx.upload_triangles(tris_h)                  # H2D of the step's input (synchronous)
+            ctx.rebuild()
+            ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=True, out=hits_h)   # D2H of the result
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+        launches_e2e = 0
+
+        # ---- sort leg: 2^26 (key, value) pairs resident in HBM ------------------------------------
+        ns = 1 << SORT_LOG2
+        g = torch.Generator(device=dev); g.manual_seed(0x5EED)
+        keys0 = torch.randint(-2 ** 31, 2 ** 31 - 1, (ns,), dtype=torch.int32, device=dev, generator=g)
+        vals0 = torch.arange(ns, dtype=torch.int32, device=dev)
+        keys = torch.empty_like(keys0); vals = torch.empty_like(vals0)
+        sort_steps = max(3, min(args.steps, 10))
+        sort_ms, pass_ms, hist_ms = [], [], []
+        for i in range(3 + sort_steps):
+            keys.copy_(keys0); vals.copy_(vals0)
+            ctx.sort_pairs_device(keys.data_ptr(), vals.data_ptr(), ns)
+            if i >= 3:
+                t = ctx.last_sort_ms()
+                sort_ms.append(t["total"]); hist_ms.append(t["histogram"])
+                pass_ms.append(statistics.mean([t["pass0"], t["pass8"], t["pass16"], t["pass24"]]))
+        torch.cuda.synchronize()
+        del keys0, vals0, keys, vals
+        s_ms, p_ms = statistics.mean(sort_ms), statistics.mean(pass_ms)
+        sort_gbs = BYTES["sort_pair"] * ns / (s_ms * 1e-3) / 1e9
+        pass_gbs = BYTES["sort_pass_pair"] * ns / (p_ms * 1e-3) / 1e9
+
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("k_onesweep_2p26_bytes_per_launch")
+            except Exception:
+                traffic = None
+
+        def roof(name, bytes_per_unit, units, ms):
+            gbs = bytes_per_unit * units / (ms * 1e-3) / 1e9
+            return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s",
+                    "frac": gbs / peak_gbs, "bytes_per_unit": bytes_per_unit, "units": units, "ms": ms}
+
+        rooflines = [
+            roof("k_morton (K1, 1M tris)", BYTES["morton"], n, stages["morton"]),
+            roof("sort total (K2: histogram + 4 passes, 1M pairs)", BYTES["sort_pair"], n, stages["sort"]),
+            roof("k_distribute_keys (K3, 1M keys)", BYTES["distribute"], n, stages["distribute"]),
+            roof("k_construct_tree (K4, 1M tris)", BYTES["tree"], n, stages["tree"]),
+            roof("k_construct_bvh (K5 + packed arrays, 1M tris)", BYTES["bvh"], n, stages["bvh"]),
+            roof("sort total (K2, 2^26 pairs)", BYTES["sort_pair"], ns, s_ms),
+        ]
+
+        # ---- CPU baseline: the oracle on a bounded sample, host cores of this box ------------------
+        from oracle import usrt_oracle as O
+        O.build()
+        threads = os.cpu_count() or 1
+        rows = 40
+        cs = cpu_step(O, tris, cam, rows, threads)
+        cpu_value = rays / cs["step_s"] / 1e6
+
+        line = {
+            "metric": "Mrays/s (1080p, 1M tris; step = full LBVH rebuild incl. sort + primary-ray cast)",
+            "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+u32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 1,048,576-tri sphere+height-field, full rebuild + 1920x1080 primary rays",
+                       "triangles": int(n), "rays_per_step_per_gpu": rays, "trace_mode": "strict (reference visiting order, no culling)",
+                       "l2": "flushed between timed steps (512 MiB write) and the scene (357 MB) exceeds the 126 MB L2",
+                       "parallelism": "1 GPU" if world == 1 else "ray-sharded x%d, replicated BVH, all-gather of hit records overlapped" % world},
+            "stages_ms": stages,
+            "trace_mrays_s": rays / (trace_ms * 1e-3) / 1e6,
+            "build_ms": stages["total"],
+            "sort": {"pairs": ns, "ms": s_ms, "mkeys_s": ns / (s_ms * 1e-3) / 1e6, "achieved_gbs": sort_gbs,
+                     "frac_of_measured_peak": sort_gbs / peak_gbs, "frac_of_8tbs": sort_gbs / 8000.0,
+                     "histogram_ms": statistics.mean(hist_ms), "pass_ms": p_ms},
+            "roofline": {"kernel": "k_onesweep (one 8-bit radix pass over 2^26 key/value pairs)", "bound": "hbm",
+                         "achieved": pass_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": pass_gbs / peak_gbs,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES["sort_pass_pair"] * ns, "ms_per_launch": p_ms},
+            "rooflines": rooflines,
+            "cpu_baseline": {"value": cpu_value, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                             "sample": "full 1M-tri rebuild on 1 thread (%.0f ms) + %d of %d rows traced on %d threads, frame "
+                                       "time extrapolated by rows" % (cs["build_s"] * 1e3, rows, H, threads)},
+            "e2e": {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(rays * 16),
+                    "note": "usrt_upload_triangles(host) + usrt_rebuild + usrt_trace_primary(host_out), pinned host buffers, 1 GPU"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "wall_s_timed_region": t_wall,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _as_tensor(torch, ptr, numel_f32, dev):
+    """Zero-copy float32 view of library-owned device memory via __cuda_array_interface__."""
+    class _Wrap:
+        pass
+    w = _Wrap()
+    w.__cuda_array_interface__ = {"shape": (int(numel_f32),), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(w, device=dev)
+
+
+def _flush_ms(torch, flush, stream):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream); flush.fill_(1); b.record(stream)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,9 @@ int usrt_rebuild(usrt_context* ctx);
  * Synchronises. Only filled when timing was enabled before the rebuild. */
 int usrt_enable_stage_timing(usrt_context* ctx, int enabled);
 int usrt_last_rebuild_ms(usrt_context* ctx, float out_ms[6]);
+/* Device time of the last sort (usrt_sort, usrt_sort_pairs_device, or the one inside usrt_rebuild), per
+ * kernel group, in ms: histogram+scan, pass bitOffset 0, 8, 16, 24, total. Synchronises. */
+int usrt_last_sort_ms(usrt_context* ctx, float out_ms[6]);
 
 /* ---- Dispatch(Raytracing) : RaytracingMeshDrawer.cs:76-84, Raytracing.compute:105-176 ---------- */
 /* K6 -- one hit record per pixel, index y*width + x, row 0 = most negative camera-space y.

@@ -1,0 +1,98 @@
+"""Error behaviour and ownership rules of the boundary on a real device."""
+import numpy as np
+import pytest
+
+from unitysimpleraytracing_b200 import _lib, meshes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_stage_order_is_enforced(usrt):
+    ctx = usrt.Context(100)
+    with pytest.raises(_lib.UsrtError) as e:
+        ctx.morton()
+    assert e.value.code == -3
+    ctx.upload_triangles(meshes.uniform_soup(50, seed=1))
+    for call in (ctx.sort, ctx.distribute_keys, ctx.construct_tree, ctx.construct_bvh):
+        with pytest.raises(_lib.UsrtError):
+            call()
+    with pytest.raises(_lib.UsrtError):
+        ctx.trace_primary(4, 4, 0.3, 0.5, np.eye(4, dtype=np.float32))
+    ctx.morton(); ctx.sort(); ctx.distribute_keys()
+    with pytest.raises(_lib.UsrtError):
+        ctx.distribute_keys()            # applying it twice would change the keys the tree is built on
+    ctx.construct_tree(); ctx.construct_bvh()
+    ctx.trace_primary(4, 4, 0.3, 0.5, np.eye(4, dtype=np.float32))
+    ctx.close()
+
+
+def test_fewer_than_two_triangles_is_rejected(usrt):
+    # BVH.compute:101 with n = 1 builds nothing and traversal would read an unwritten root box
+    ctx = usrt.Context(10)
+    ctx.upload_triangles(meshes.uniform_soup(1, seed=2))
+    with pytest.raises(_lib.UsrtError) as e:
+        ctx.rebuild()
+    assert e.value.code == -1
+    ctx.close()
+
+
+def test_capacity_is_enforced(usrt):
+    ctx = usrt.Context(10)
+    with pytest.raises(_lib.UsrtError):
+        ctx.upload_triangles(meshes.uniform_soup(11, seed=3))
+    ctx.close()
+
+
+def test_two_contexts_are_independent(usrt, oracle):
+    a, b = meshes.uniform_soup(3000, seed=4), meshes.uniform_soup(2000, seed=5)
+    ca, cb = usrt.Context(3000), usrt.Context(2000)
+    ca.upload_triangles(a); cb.upload_triangles(b)
+    ca.rebuild(); cb.rebuild()
+    ra, rb = oracle.Scene(a), oracle.Scene(b)
+    assert ca.download(_lib.BUF_BVH_DATA, 2999).tobytes() == ra.bvhData[:2999].tobytes()
+    assert cb.download(_lib.BUF_BVH_DATA, 1999).tobytes() == rb.bvhData[:1999].tobytes()
+    ca.close(); cb.close()
+
+
+def test_world_bounds_override(usrt, oracle):
+    tris = meshes.uniform_soup(5000, seed=6, extent=10.0)
+    ctx = usrt.Context(5000)
+    ctx.set_world_bounds(-16.0, 16.0)
+    ctx.upload_triangles(tris); ctx.morton()
+    want, _, _ = oracle.morton(tris, -16.0, 16.0)
+    assert np.array_equal(ctx.download(_lib.BUF_KEYS), want)
+    ctx.close()
+
+
+def test_stage_timing_and_launch_counter(usrt):
+    ctx = usrt.Context(70000)
+    ctx.upload_triangles(meshes.scene_c1())
+    ctx.enable_stage_timing(True)
+    before = ctx.kernel_launches
+    ctx.rebuild()
+    ms = ctx.last_rebuild_ms()
+    assert ctx.kernel_launches - before >= 9
+    assert 0 < ms["total"] < 50 and abs(sum(ms[k] for k in ("morton", "sort", "distribute", "tree", "bvh")) - ms["total"]) < 0.05
+    ctx.close()
+
+
+def test_runs_on_a_torch_stream_with_device_buffers(usrt, oracle):
+    import torch
+    tris = meshes.uniform_soup(4000, seed=8)
+    ref = oracle.Scene(tris)
+    dev = torch.device("cuda:0")
+    ctx = usrt.Context(4000)
+    s = torch.cuda.Stream()
+    ctx.set_stream(s.cuda_stream)
+    with torch.cuda.stream(s):
+        t = torch.from_numpy(tris.view(np.uint8).reshape(-1)).to(dev)
+        ctx.set_triangles_device(t.data_ptr(), len(tris))
+        ctx.rebuild()
+        rays = meshes.incoherent_rays(1000, seed=3)
+        tr = torch.from_numpy(rays).to(dev)
+        out = torch.empty(1000 * 4, dtype=torch.float32, device=dev)
+        ctx.trace_rays_device(tr.data_ptr(), 1000, out.data_ptr())
+    s.synchronize()
+    got = out.cpu().numpy().view(oracle.RAYCAST_RESULT)
+    assert got.tobytes() == ref.trace_rays(rays).tobytes()
+    ctx.close()

@@ -1,0 +1,235 @@
+"""CPU tests of the oracle itself: the reference's runtime self-checks restated as
+unit tests, the C++ twin against an independent numpy restatement, and structural invariants."""
+import numpy as np
+import pytest
+
+from oracle import np_oracle as NP
+from unitysimpleraytracing_b200 import meshes
+
+
+def _keys(kind, n, seed=1):
+    rng = np.random.default_rng(seed)
+    if kind == "uniform":
+        return rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    if kind == "morton30":
+        return rng.integers(0, 2 ** 30, n, dtype=np.uint64).astype(np.uint32)
+    if kind == "low":
+        return (rng.integers(0, 5, n, dtype=np.uint64) * 0x01000100).astype(np.uint32)
+    if kind == "equal":
+        return np.full(n, 0xCAFEF00D, np.uint32)
+    if kind == "padded":                     # real keys followed by 0xFFFFFFFF padding (MeshBufferContainer.cs:108-109)
+        k = rng.integers(0, 2 ** 30, n, dtype=np.uint64).astype(np.uint32)
+        k[n // 2:] = 0xFFFFFFFF
+        return k
+    raise ValueError(kind)
+
+
+# ---- Morton / AABB ---------------------------------------------------------------------------------
+def test_morton_known_answers(oracle):
+    # ExpandBits/Morton3D (MeshBufferContainer.cs:32-50): x is the most significant bit of each triple
+    t = np.zeros(4, oracle.TRIANGLE)
+    pts = np.array([[-125, -125, -125], [125, 125, 125], [0, -125, -125], [-125, -125, 0]], np.float32)
+    for f in "abc":
+        t[f] = pts
+    keys, values, aabb = oracle.morton(t)
+    # centroid == the point; (p+125)/250*1024 -> 0, 1024->clamped 1023, 512
+    assert keys[0] == 0
+    assert keys[1] == 0x3FFFFFFF
+    assert keys[2] == 0b100 << 27            # x = 512 = bit 9 -> key bit 3*9+2
+    assert keys[3] == 0b001 << 27            # z = 512 -> key bit 27
+    assert list(values) == [0, 1, 2, 3]
+    assert np.allclose(aabb["min"][0], -125.001) and np.allclose(aabb["max"][0], -124.999)
+    assert (aabb["_dummy0"] == 0).all() and (aabb["_dummy1"] == 0).all()
+
+
+@pytest.mark.parametrize("mesh", ["soup", "grid", "sphere", "outside"])
+def test_morton_matches_numpy_restatement(oracle, mesh):
+    tris = {"soup": lambda: meshes.uniform_soup(5000, seed=3),
+            "grid": meshes.reference_scene_grid,
+            "sphere": lambda: meshes.sphere(24, 48),
+            "outside": lambda: meshes.uniform_soup(3000, seed=4, extent=200.0)}[mesh]()   # clamps to 0 / 1023
+    keys, values, aabb = oracle.morton(tris)
+    k2, mn, mx = NP.morton_and_aabb(tris["a"], tris["b"], tris["c"])
+    assert np.array_equal(keys, k2)
+    assert aabb["min"].tobytes() == mn.tobytes() and aabb["max"].tobytes() == mx.tobytes()
+    assert np.array_equal(values, np.arange(len(tris), dtype=np.uint32))
+    assert keys.max() < 2 ** 30
+
+
+def test_reference_scene_has_many_duplicate_keys(oracle):
+    # the shipped 12,800-triangle grid falls into ~1,156 Morton cells -- why DistributeKeys exists
+    keys, _, _ = oracle.morton(meshes.reference_scene_grid())
+    assert len(keys) == 12800
+    assert 1000 < len(np.unique(keys)) < 1400
+
+
+# ---- sort: the reference's validators (ComputeBufferSorter.cs:150-272) -------------------------------
+@pytest.mark.parametrize("kind", ["uniform", "morton30", "low", "equal", "padded"])
+@pytest.mark.parametrize("n", [1024, 8192])
+def test_sort_pass_validators(oracle, kind, n):
+    keys = _keys(kind, n)
+    values = np.arange(n, dtype=np.uint32)
+    nb = n // 1024
+    for bit_offset in (0, 8, 16, 24):
+        r = oracle.sort_pass(keys, values, bit_offset)
+        radix = lambda k: (k >> np.uint32(bit_offset)) & np.uint32(255)
+        # ValidateIntermediateData part 1 (:200-218): per-digit multiset preserved by the block sort
+        assert np.array_equal(np.bincount(radix(r["sortedBlocksKeys"]), minlength=256),
+                              np.bincount(radix(keys), minlength=256))
+        # part 2 (:227-254): per block b, digit k: count == sizesBefore[b + k*numBlocks]
+        blocks = radix(r["sortedBlocksKeys"]).reshape(nb, 1024)
+        for b in range(nb):
+            assert np.array_equal(np.bincount(blocks[b], minlength=256), r["sizesBefore"][b::nb][:256])
+            assert (np.diff(blocks[b].astype(np.int64)) >= 0).all()       # block is digit-sorted
+        # part 3 (:256-271): exclusive-scan identity
+        assert r["sizesAfter"][0] == 0
+        assert np.array_equal(r["sizesAfter"][1:], (r["sizesBefore"][:-1] + r["sizesAfter"][:-1]).astype(np.uint32))
+        # the pass is a stable sort by this digit
+        order = np.argsort(radix(keys), kind="stable")
+        assert np.array_equal(r["keys"], keys[order]) and np.array_equal(r["values"], values[order])
+        keys, values = r["keys"], r["values"]
+    # ValidateSortedData (:150-177): non-decreasing
+    assert (np.diff(keys.astype(np.int64)) >= 0).all()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "morton30", "low", "equal", "padded"])
+@pytest.mark.parametrize("n", [0, 1, 2, 1023, 1025, 5000, 70001])
+def test_sort_is_stable_sort_by_key(oracle, kind, n):
+    keys = _keys(kind, n, seed=n + 5)
+    values = np.arange(n, dtype=np.uint32)[::-1].copy()
+    k, v = oracle.sort(keys, values)
+    k2, v2 = oracle.stable_sort(keys, values)
+    k3, v3 = NP.stable_sort(keys, values)
+    assert np.array_equal(k, k2) and np.array_equal(v, v2)
+    assert np.array_equal(k, k3) and np.array_equal(v, v3)
+
+
+# ---- DistributeKeys -------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["uniform", "morton30", "low", "equal"])
+def test_distribute_keys(oracle, kind):
+    keys = np.sort(_keys(kind, 4000))
+    d = oracle.distribute_keys(keys)
+    assert np.array_equal(d, NP.distribute_keys(keys))
+    assert d[0] == 0
+    if kind != "uniform":     # no wraparound possible below 2^31
+        assert (np.diff(d.astype(np.int64)) > 0).all()
+
+
+def test_distribute_keys_wraps_like_unchecked_uint(oracle):
+    # unsorted input (misuse) still follows C# unchecked arithmetic: max(k[i]-k[i-1] mod 2^32, 1)
+    keys = np.array([10, 5, 5, 0xFFFFFFF0, 3], np.uint32)
+    want = np.array([0, 0xFFFFFFFB, 0xFFFFFFFC, 0xFFFFFFE7, 0xFFFFFFFA], np.uint32)
+    assert np.array_equal(oracle.distribute_keys(keys), want)
+    assert np.array_equal(NP.distribute_keys(keys), want)
+
+
+def test_distribute_keys_only_touches_triangles_length(oracle):
+    keys = np.array([1, 1, 4, 0xFFFFFFFF, 0xFFFFFFFF], np.uint32)
+    assert list(oracle.distribute_keys(keys, n=3)) == [0, 1, 4, 0xFFFFFFFF, 0xFFFFFFFF]
+
+
+# ---- tree + refit ---------------------------------------------------------------------------------
+def _check_tree_invariants(internal, leaf, n):
+    # every internal has two children, parent/child reciprocity, leaf.index == position,
+    # in-order leaf sequence == 0..n-1, root = node 0 with parent NullLeaf
+    assert internal["parent"][0] == 0xFFFFFFFF
+    assert np.array_equal(internal["index"][:n - 1], np.arange(n - 1, dtype=np.uint32))
+    assert np.array_equal(leaf["index"][:n], np.arange(n, dtype=np.uint32))
+    for side in ("left", "right"):
+        c, t = internal[side + "Node"][:n - 1], internal[side + "NodeType"][:n - 1]
+        assert set(np.unique(t)) <= {0, 1}
+        ii = np.nonzero(t == 0)[0]; ll = np.nonzero(t == 1)[0]
+        assert np.array_equal(internal["parent"][c[ii]], ii.astype(np.uint32))
+        assert np.array_equal(leaf["parent"][c[ll]], ll.astype(np.uint32))
+    kids_i = np.concatenate([internal[s + "Node"][:n - 1][internal[s + "NodeType"][:n - 1] == 0] for s in ("left", "right")])
+    kids_l = np.concatenate([internal[s + "Node"][:n - 1][internal[s + "NodeType"][:n - 1] == 1] for s in ("left", "right")])
+    assert np.array_equal(np.sort(kids_i), np.arange(1, n - 1, dtype=np.uint32))      # every non-root internal once
+    assert np.array_equal(np.sort(kids_l), np.arange(n, dtype=np.uint32))            # every leaf once
+    order, stack = [], [(0, 0)]
+    while stack:
+        node, typ = stack.pop()
+        if typ == 1:
+            order.append(node)
+        else:
+            stack.append((int(internal["rightNode"][node]), int(internal["rightNodeType"][node])))
+            stack.append((int(internal["leftNode"][node]), int(internal["leftNodeType"][node])))
+    assert order == list(range(n))
+
+
+@pytest.mark.parametrize("mesh,n", [("soup", 2), ("soup", 3), ("soup", 257), ("soup", 3000), ("grid", 12800)])
+def test_tree_and_refit_match_topdown_restatement(oracle, mesh, n):
+    tris = meshes.uniform_soup(n, seed=11) if mesh == "soup" else meshes.reference_scene_grid()
+    s = oracle.Scene(tris)
+    n = s.n
+    _check_tree_invariants(s.internalNodes, s.leafNodes, n)
+    it, lf = NP.radix_tree_topdown(s.sortedMortonCodes)
+    assert np.array_equal(s.internalNodes.view(np.uint32).reshape(-1, 6)[:n - 1], it[:n - 1])
+    assert np.array_equal(s.leafNodes.view(np.uint32).reshape(-1, 2), lf)
+    bmin, bmax = NP.refit_recursive(it, s.sortedTriangleIndices, s.triangleAABB["min"], s.triangleAABB["max"])
+    assert s.bvhData["min"][:n - 1].tobytes() == bmin[:n - 1].tobytes()
+    assert s.bvhData["max"][:n - 1].tobytes() == bmax[:n - 1].tobytes()
+    assert (s.bvhData["_dummy0"] == 0).all() and (s.bvhData["_dummy1"] == 0).all()
+    # root box == union of all triangle boxes (SURVEY 8c iv)
+    assert np.array_equal(s.bvhData["min"][0], s.triangleAABB["min"].min(0))
+    assert np.array_equal(s.bvhData["max"][0], s.triangleAABB["max"].max(0))
+
+
+def test_tree_depth_bounded_by_key_width(oracle):
+    # unique 32-bit keys => depth <= 32 => the 64-entry stack (Raytracing.compute:133) cannot overflow
+    s = oracle.Scene(meshes.reference_scene_grid())
+    d, stack = 0, [(0, 1)]
+    while stack:
+        node, dep = stack.pop()
+        d = max(d, dep)
+        for side in ("left", "right"):
+            if s.internalNodes[side + "NodeType"][node] == 0:
+                stack.append((int(s.internalNodes[side + "Node"][node]), dep + 1))
+    assert d <= 33
+
+
+# ---- traversal ------------------------------------------------------------------------------------
+def test_miss_sentinel_is_not_flt_max(oracle):
+    assert oracle.max_float().view(np.uint32) == 0x4EFF0000 and float(oracle.max_float()) == 2139095040.0
+
+
+@pytest.mark.parametrize("mesh", ["soup", "grid"])
+def test_traversal_equals_brute_force_in_visit_order(oracle, mesh):
+    # BVH walk == brute force over all triangles in the walk's visiting order
+    if mesh == "soup":
+        s = oracle.Scene(meshes.uniform_soup(2000, seed=21)); cam = meshes.SCENE_SOUP_CAMERA
+    else:
+        s = oracle.Scene(meshes.reference_scene_grid()); cam = meshes.REFERENCE_CAMERA
+    rays = np.concatenate([oracle.primary_rays(24, 24, cam["near"], cam["tan_half_fov"], cam["cam_to_world"]),
+                           meshes.incoherent_rays(300, seed=5, extent=4.0 if mesh == "grid" else 100.0)])
+    got = s.trace_rays(rays)
+    order = s.visit_order()
+    assert np.array_equal(np.sort(order), np.arange(s.n, dtype=np.uint32))
+    bf = s.brute_force(rays, order=order)
+    assert got.tobytes() == bf.tobytes()
+    # and against the independent numpy brute force
+    t = s.triangleData
+    ref = NP.brute_force_hits(rays[:, 0:3], rays[:, 4:7], t["a"], t["b"], t["c"], s.triangleAABB["min"],
+                              s.triangleAABB["max"], order, oracle.max_float())
+    for g, (dist, tri, u, v) in zip(got, ref):
+        assert g["distance"].view(np.uint32) == np.float32(dist).view(np.uint32)
+        assert g["triangleIndex"] == tri
+        assert g["uv"][0].view(np.uint32) == np.float32(u).view(np.uint32)
+        assert g["uv"][1].view(np.uint32) == np.float32(v).view(np.uint32)
+    assert (got["distance"] != oracle.max_float()).sum() > 50
+
+
+def test_primary_trace_equals_ray_buffer_trace(oracle):
+    s = oracle.Scene(meshes.uniform_soup(1500, seed=31)); cam = meshes.SCENE_SOUP_CAMERA
+    a = s.trace_primary(40, 30, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], threads=2)
+    b = s.trace_rays(oracle.primary_rays(40, 30, cam["near"], cam["tan_half_fov"], cam["cam_to_world"]))
+    assert a.tobytes() == b.tobytes()
+
+
+def test_row_zero_is_bottom_of_view(oracle):
+    # Raytracing.compute:116: id.y = 0 maps to the most negative camera-space y
+    cam = meshes.REFERENCE_CAMERA
+    rays = oracle.primary_rays(8, 8, cam["near"], cam["tan_half_fov"], cam["cam_to_world"]).reshape(8, 8, 8)
+    assert (rays[0, :, 5] < 0).all() and (rays[7, :, 5] > 0).all()
+    assert np.allclose(rays[:, :, 0:3], [0, 0, 15.7])
+    assert np.allclose(np.linalg.norm(rays[:, :, 4:7], axis=2), 1.0, atol=1e-6)
+    assert (rays[:, :, 6] < 0).all()          # the scene camera looks down world -z (Scene.unity:342)

@@ -1,0 +1,179 @@
+"""GPU parity tests proper: every stage of the CUDA path, called through the C ABI, against the
+oracle on the same seeded inputs. Bit-exact for keys, indices, topology and boxes; hit records are
+compared bit-for-bit as well (the north_star tolerance is 1e-5 relative on distance -- the arithmetic
+is defined op-for-op on both sides, so exact equality is what we assert)."""
+import numpy as np
+import pytest
+
+from unitysimpleraytracing_b200 import _lib, meshes
+
+pytestmark = pytest.mark.gpu
+
+
+def _mesh(name):
+    if name == "soup2":
+        return meshes.uniform_soup(2, seed=41)
+    if name == "soup3":
+        return meshes.uniform_soup(3, seed=42)
+    if name == "soup4097":
+        return meshes.uniform_soup(4097, seed=43)
+    if name == "refgrid":
+        return meshes.reference_scene_grid()
+    if name == "sphere":
+        return meshes.sphere(96, 192)
+    if name == "c1":
+        return meshes.scene_c1()
+    if name == "outside":               # centroids beyond the +-125 world box clamp to 0 / 1023
+        return meshes.uniform_soup(20000, seed=44, extent=190.0)
+    if name == "identical":             # every key equal: DistributeKeys spreads them 0,1,2,...
+        t = meshes.uniform_soup(1, seed=45)
+        return np.repeat(t, 3001)
+    if name == "degenerate":            # zero-area and point triangles mixed in
+        t = meshes.uniform_soup(5000, seed=46)
+        t["b"][::3] = t["a"][::3]
+        t["c"][::7] = t["a"][::7]
+        return t
+    raise ValueError(name)
+
+
+MESHES = ["soup2", "soup3", "soup4097", "refgrid", "sphere", "c1", "outside", "identical", "degenerate"]
+
+
+def _same(a, b):
+    return np.ascontiguousarray(a).tobytes() == np.ascontiguousarray(b).tobytes()
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_build_stage_by_stage(usrt, oracle, name):
+    """The reference's Awake() sequence (RaytracingMeshDrawer.cs:34-51), one entry point at a time."""
+    tris = _mesh(name)
+    n = len(tris)
+    ref = oracle.Scene(tris)
+    c = usrt.MeshBufferContainer(tris, capacity=n + 1000)        # capacity > n: padding slots stay 0xFFFFFFFF
+    ctx = c.ctx
+    assert c.TrianglesLength == n
+    assert np.array_equal(c.Keys.GetData(n), ref.mortonCodes)
+    assert np.array_equal(c.TriangleIndex.GetData(n), np.arange(n, dtype=np.uint32))
+    assert _same(c.TriangleAABB.GetData(n), ref.triangleAABB)
+
+    usrt.ComputeBufferSorter(c.TrianglesLength, c.Keys, c.TriangleIndex).Sort()
+    assert np.array_equal(c.Keys.GetData(n), ref.sortedMortonRaw)
+    assert np.array_equal(c.TriangleIndex.GetData(n), ref.sortedTriangleIndices)
+    full_keys = c.Keys.GetData(n + 1000)
+    assert (full_keys[n:] == 0xFFFFFFFF).all() and (c.TriangleIndex.GetData(n + 1000)[n:] == 0xFFFFFFFF).all()
+
+    c.DistributeKeys()
+    assert np.array_equal(c.Keys.GetData(n), ref.sortedMortonCodes)
+    assert (c.Keys.GetData(n + 1000)[n:] == 0xFFFFFFFF).all()
+
+    b = usrt.BVHConstructor(c.TrianglesLength, c.Keys, c.TriangleIndex, c.TriangleAABB, c.BvhInternalNode,
+                            c.BvhLeafNode, c.BvhData)
+    b.ConstructTree()
+    assert _same(c.BvhInternalNode.GetData(n - 1), ref.internalNodes[:n - 1])
+    assert _same(c.BvhLeafNode.GetData(n), ref.leafNodes)
+    # untouched slots keep NullLeaf (MeshBufferContainer.cs:114-115)
+    assert (c.BvhInternalNode.GetData(n + 10).view(np.uint32).reshape(-1, 6)[n - 1:] == 0xFFFFFFFF).all()
+    assert (c.BvhLeafNode.GetData(n + 10).view(np.uint32).reshape(-1, 2)[n:] == 0xFFFFFFFF).all()
+    b.ConstructBVH()
+    assert _same(c.BvhData.GetData(n - 1), ref.bvhData[:n - 1])
+    assert c.GetAllGpuData() == (0, 0)                          # MeshBufferContainer.cs:181-195
+    assert ctx.count_corrupted_nodes() == (0, 0)
+    b.ConstructBVH()                                             # re-runnable (self-resetting counters)
+    assert _same(c.BvhData.GetData(n - 1), ref.bvhData[:n - 1])
+    c.Dispose()
+
+
+@pytest.mark.parametrize("name", ["soup4097", "refgrid", "c1", "identical"])
+def test_fused_rebuild_equals_stages_and_is_repeatable(usrt, oracle, name):
+    tris = _mesh(name)
+    n = len(tris)
+    ref = oracle.Scene(tris)
+    ctx = usrt.Context(n)
+    ctx.upload_triangles(tris)
+    for _ in range(3):
+        ctx.rebuild()
+        assert np.array_equal(ctx.download(_lib.BUF_KEYS), ref.sortedMortonCodes)
+        assert np.array_equal(ctx.download(_lib.BUF_TRIANGLE_INDEX), ref.sortedTriangleIndices)
+        assert _same(ctx.download(_lib.BUF_INTERNAL_NODES, n - 1), ref.internalNodes[:n - 1])
+        assert _same(ctx.download(_lib.BUF_LEAF_NODES), ref.leafNodes)
+        assert _same(ctx.download(_lib.BUF_BVH_DATA, n - 1), ref.bvhData[:n - 1])
+    # a smaller mesh in the same context: stale nodes must not leak
+    small = meshes.uniform_soup(max(n // 3, 2), seed=77)
+    ref2 = oracle.Scene(small)
+    ctx.upload_triangles(small)
+    ctx.rebuild()
+    m = len(small)
+    assert _same(ctx.download(_lib.BUF_INTERNAL_NODES, m - 1), ref2.internalNodes[:m - 1])
+    assert _same(ctx.download(_lib.BUF_BVH_DATA, m - 1), ref2.bvhData[:m - 1])
+    assert (ctx.download(_lib.BUF_INTERNAL_NODES, n).view(np.uint32).reshape(-1, 6)[m - 1:] == 0xFFFFFFFF).all()
+    ctx.close()
+
+
+def _report_ties(got, want):
+    """IDs must be exact; where they differ but the distances are equal it is an edge/vertex tie,
+    counted separately (north_star). Returns (id_mismatches_not_ties, ties)."""
+    bad = got["triangleIndex"] != want["triangleIndex"]
+    ties = bad & (got["distance"] == want["distance"])
+    return int((bad & ~ties).sum()), int(ties.sum())
+
+
+@pytest.mark.parametrize("name,cam,w,h", [
+    ("soup4097", "SCENE_SOUP_CAMERA", 160, 90), ("refgrid", "REFERENCE_CAMERA", 160, 90),
+    ("sphere", "SCENE_C2_CAMERA", 192, 108), ("c1", "SCENE_SOUP_CAMERA", 128, 128),
+    ("degenerate", "SCENE_SOUP_CAMERA", 96, 96), ("identical", "SCENE_SOUP_CAMERA", 33, 17),
+    ("soup2", "SCENE_SOUP_CAMERA", 31, 9)])
+def test_primary_rays(usrt, oracle, name, cam, w, h):
+    tris = _mesh(name)
+    cam = getattr(meshes, cam)
+    ref = oracle.Scene(tris)
+    want = ref.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], threads=8)
+    d = usrt.RaytracingMeshDrawer(tris).Awake()
+    got = d.Update(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    assert _report_ties(got, want) == (0, 0)
+    assert np.array_equal(got["triangleIndex"], want["triangleIndex"])
+    hit = want["distance"] != oracle.max_float()
+    rel = np.abs(got["distance"][hit] - want["distance"][hit]) / np.maximum(np.abs(want["distance"][hit]), 1e-30)
+    assert (rel <= 1e-5).all()                                   # the north_star bar ...
+    assert _same(got, want)                                      # ... and what actually holds: bit-exact
+    assert np.array_equal(got["distance"][~hit].view(np.uint32), np.full((~hit).sum(), 0x4EFF0000, np.uint32))
+    # row sharding hook: two half-frames == the full frame
+    ctx = d.container.ctx
+    out = np.zeros(w * h, got.dtype)
+    ctx.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], 0, h // 2, out=out)
+    ctx.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], h // 2, h, out=out)
+    assert _same(out, want)
+    d.OnDestroy()
+
+
+@pytest.mark.parametrize("name,extent,count", [("c1", 100.0, 20000), ("refgrid", 4.0, 5000), ("sphere", 60.0, 5000)])
+def test_incoherent_rays(usrt, oracle, name, extent, count):
+    """Random-origin random-direction rays (config 4's stress shape): origins inside the geometry, hits
+    behind the origin (negative t is accepted by the reference), axis-aligned directions (inv_dir = inf)."""
+    tris = _mesh(name)
+    ref = oracle.Scene(tris)
+    rays = meshes.incoherent_rays(count, seed=9, extent=extent)
+    rays[:50, 4:7] = [0, 0, -1]           # inv_dir = (inf, inf, -1): the 0*inf = NaN slab cases
+    rays[50:100, 4:7] = [1, 0, 0]
+    rays[100:120, 0:3] = tris["a"][:20]   # origins exactly on vertices
+    want = ref.trace_rays(rays, threads=8)
+    d = usrt.RaytracingMeshDrawer(tris).Awake()
+    got = d.container.ctx.trace_rays(rays)
+    assert _report_ties(got, want) == (0, 0)
+    assert _same(got, want)
+    assert (want["distance"] != oracle.max_float()).sum() > 10
+    d.OnDestroy()
+
+
+def test_culled_mode_is_reported_separately(usrt, oracle):
+    """Mode 1 is NOT part of the parity contract; it must still find a hit wherever strict does, never
+    a farther one by more than fp noise. We only record how far it is from strict."""
+    tris = _mesh("c1"); cam = meshes.SCENE_SOUP_CAMERA
+    d = usrt.RaytracingMeshDrawer(tris).Awake()
+    strict = d.Update(128, 128, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    d.container.ctx.set_trace_mode(1)
+    culled = d.Update(128, 128, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    d.container.ctx.set_trace_mode(0)
+    assert np.array_equal(strict["distance"] == oracle.max_float(), culled["distance"] == oracle.max_float())
+    differing = int((strict["triangleIndex"] != culled["triangleIndex"]).sum())
+    assert differing <= len(strict) // 1000
+    d.OnDestroy()

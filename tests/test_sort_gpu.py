@@ -1,0 +1,87 @@
+"""Standalone key/value sorter (ComputeBufferSorter<uint,uint>) on the GPU: exact against the oracle
+at small sizes, and size-independent properties at BASELINE config-3 sizes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _keys(kind, n, seed=1):
+    rng = np.random.default_rng(seed)
+    if kind == "uniform":
+        return rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    if kind == "morton30":
+        return rng.integers(0, 2 ** 30, n, dtype=np.uint64).astype(np.uint32)
+    if kind == "low":
+        return (rng.integers(0, 5, n, dtype=np.uint64) * 0x01000100).astype(np.uint32)
+    if kind == "equal":
+        return np.full(n, 0xCAFEF00D, np.uint32)
+    if kind == "allmax":
+        return np.full(n, 0xFFFFFFFF, np.uint32)
+    if kind == "sorted":
+        return np.sort(rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32))
+    if kind == "reverse":
+        return np.sort(rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32))[::-1].copy()
+    raise ValueError(kind)
+
+
+KINDS = ["uniform", "morton30", "low", "equal", "allmax", "sorted", "reverse"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n", [0, 1, 2, 33, 1024, 4095, 4096, 4097, 70001, 1 << 20])
+def test_sort_pairs_matches_oracle(usrt, oracle, kind, n):
+    keys = _keys(kind, n, seed=n + 3)
+    values = np.arange(n, dtype=np.uint32)[::-1].copy()
+    want_k, want_v = oracle.sort(keys, values) if n <= 70001 else oracle.stable_sort(keys, values)
+    k, v = keys.copy(), values.copy()
+    usrt.ComputeBufferSorter(n, k, v).Sort()
+    assert np.array_equal(k, want_k)
+    assert np.array_equal(v, want_v)
+
+
+def test_sort_keys_only(usrt):
+    keys = _keys("uniform", 300000)
+    k = keys.copy()
+    ctx = usrt.Context(2)
+    ctx.sort_pairs_host(k, None)
+    assert np.array_equal(k, np.sort(keys))
+    ctx.close()
+
+
+@pytest.mark.parametrize("log2n,kind", [(24, "uniform"), (26, "uniform"), (26, "morton30"), (24, "low")])
+def test_sort_properties_at_scale(usrt, log2n, kind):
+    """2^24..2^26 pairs: sortedness, stability, permutation (checksum of checksums) -- no O(n log n) CPU."""
+    n = 1 << log2n
+    keys = _keys(kind, n, seed=log2n)
+    values = np.arange(n, dtype=np.uint32)
+    k, v = keys.copy(), values.copy()
+    ctx = usrt.Context(2)
+    ctx.sort_pairs_host(k, v)
+    ctx.close()
+    dk = np.diff(k.astype(np.int64))
+    assert (dk >= 0).all()                                            # ValidateSortedData (:150-177)
+    assert (np.diff(v.astype(np.int64))[dk == 0] > 0).all()           # stable: equal keys keep input order
+    assert np.array_equal(keys[v], k)                                 # each pair travelled together
+    assert int(v.astype(np.uint64).sum()) == n * (n - 1) // 2         # values are a permutation ...
+    assert int((v.astype(np.uint64) ** 2 % 1000003).sum()) == int((values.astype(np.uint64) ** 2 % 1000003).sum())
+    assert np.array_equal(np.bincount(k >> 24, minlength=256), np.bincount(keys >> 24, minlength=256))
+
+
+def test_partition_pass_is_stable_split_by_top_byte(usrt):
+    import torch
+    n = 200003
+    keys = _keys("uniform", n)
+    values = np.arange(n, dtype=np.uint32)
+    dev = torch.device("cuda:0")
+    tk = torch.from_numpy(keys.view(np.int32)).to(dev); tv = torch.from_numpy(values.view(np.int32)).to(dev)
+    ok = torch.empty_like(tk); ov = torch.empty_like(tv); hist = torch.zeros(256, dtype=torch.int32, device=dev)
+    ctx = usrt.Context(2)
+    torch.cuda.synchronize()
+    ctx.partition_pass_device(tk.data_ptr(), tv.data_ptr(), ok.data_ptr(), ov.data_ptr(), n, 24, hist.data_ptr())
+    ctx.sync()
+    order = np.argsort(keys >> 24, kind="stable")
+    assert np.array_equal(ok.cpu().numpy().view(np.uint32), keys[order])
+    assert np.array_equal(ov.cpu().numpy().view(np.uint32), values[order])
+    assert np.array_equal(hist.cpu().numpy(), np.bincount(keys >> 24, minlength=256))
+    ctx.close()

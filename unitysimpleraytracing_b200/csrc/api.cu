@@ -52,6 +52,8 @@ struct usrt_context {
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
+    cudaEvent_t sort_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool sort_ev_valid = false;
 
     uint64_t launches = 0;
     char err[512] = {0};
@@ -131,8 +133,10 @@ int do_morton(usrt_context* ctx) {
 }
 
 int do_sort(usrt_context* ctx) {
+    ctx->sort_ev_valid = false;
     CU(ctx, sort_pairs(ctx->keys, ctx->tri_index, ctx->keys_alt, ctx->tri_index_alt, ctx->n, ctx->sort, ctx->stream,
-                       &ctx->launches));
+                       &ctx->launches, ctx->timing ? ctx->sort_ev : nullptr));
+    ctx->sort_ev_valid = ctx->timing && ctx->n > 0;
     ctx->stage |= ST_SORTED;
     return USRT_OK;
 }
@@ -200,6 +204,7 @@ int usrt_create(int device, uint32_t capacity, usrt_context** out) {
         CU(ctx, sort_scratch_reserve(ctx->sort, capacity, false));
         CU(ctx, cudaMemsetAsync(ctx->triangles, 0, c * sizeof(usrt_triangle), ctx->stream));
         for (auto& ev : ctx->ev) CU(ctx, cudaEventCreate(&ev));
+        for (auto& ev : ctx->sort_ev) CU(ctx, cudaEventCreate(&ev));
         int r = reset_scene_buffers(ctx);
         if (r != USRT_OK) return r;
         CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -226,6 +231,8 @@ int usrt_destroy(usrt_context* ctx) {
         if (p) cudaFree(p);
     sort_scratch_free(ctx->sort);
     for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->sort_ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -304,8 +311,10 @@ int usrt_sort_pairs_device(usrt_context* ctx, uint32_t* dev_keys, uint32_t* dev_
     if (count >= (1ull << 32)) return fail(ctx, USRT_ERR_ARG, "sort_pairs: count must be < 2^32");
     if (int r = bind_device(ctx)) return r;
     CU(ctx, sort_scratch_reserve(ctx->sort, std::max<uint64_t>(count, 1), true));
+    ctx->sort_ev_valid = false;
     CU(ctx, sort_pairs(dev_keys, dev_values, ctx->sort.keys_alt, dev_values ? ctx->sort.vals_alt : nullptr, count,
-                       ctx->sort, ctx->stream, &ctx->launches));
+                       ctx->sort, ctx->stream, &ctx->launches, ctx->timing ? ctx->sort_ev : nullptr));
+    ctx->sort_ev_valid = ctx->timing && count > 0;
     return USRT_OK;
 }
 
@@ -409,6 +418,17 @@ int usrt_last_rebuild_ms(usrt_context* ctx, float out_ms[6]) {
     CU(ctx, cudaEventSynchronize(ctx->ev[5]));
     for (int i = 0; i < 5; ++i) CU(ctx, cudaEventElapsedTime(&out_ms[i], ctx->ev[i], ctx->ev[i + 1]));
     CU(ctx, cudaEventElapsedTime(&out_ms[5], ctx->ev[0], ctx->ev[5]));
+    return USRT_OK;
+}
+
+int usrt_last_sort_ms(usrt_context* ctx, float out_ms[6]) {
+    NEED_CTX(ctx);
+    if (!out_ms) return USRT_ERR_ARG;
+    if (!ctx->sort_ev_valid) return fail(ctx, USRT_ERR_STATE, "last_sort_ms: no timed sort");
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, cudaEventSynchronize(ctx->sort_ev[5]));
+    for (int i = 0; i < 5; ++i) CU(ctx, cudaEventElapsedTime(&out_ms[i], ctx->sort_ev[i], ctx->sort_ev[i + 1]));
+    CU(ctx, cudaEventElapsedTime(&out_ms[5], ctx->sort_ev[0], ctx->sort_ev[5]));
     return USRT_OK;
 }
 

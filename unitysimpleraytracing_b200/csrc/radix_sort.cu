@@ -20,10 +20,12 @@ namespace usrt {
 
 namespace {
 
-constexpr int kBlock = 256;                 // threads per tile CTA (8 warps)
+constexpr int kBlock = 512;                 // threads per tile CTA (16 warps)
 constexpr int kIPT = 16;                    // pairs per thread
-constexpr int kTile = kBlock * kIPT;        // 4096 pairs per tile
+constexpr int kTile = kBlock * kIPT;        // 8192 pairs per tile
 constexpr int kWarps = kBlock / 32;
+constexpr int kCtasPerSM = 2;
+static_assert(kBlock >= kRadix, "one thread per digit in the scan / look-back step");
 constexpr uint32_t kHeaderWords = 64;       // tile counters live in the first 256 B of the status buffer
 
 // look-back status word: flag in the top bits, running count below. 32-bit words hold counts
@@ -41,17 +43,25 @@ template <> struct StatusTraits<uint64_t> {
 };
 
 // ---- upfront histogram: all four digits from one read of the keys --------------------------------
-__global__ void __launch_bounds__(256) k_histogram(const uint32_t* __restrict__ keys, uint64_t n,
-                                                   uint32_t* __restrict__ hist /* [4][256], zeroed */) {
-    __shared__ uint32_t s_hist[kSortPasses * kRadix];
-    for (int i = threadIdx.x; i < kSortPasses * kRadix; i += blockDim.x) s_hist[i] = 0;
+// One persistent 1024-thread CTA per SM. Shared-memory counters are laid out [pass][digit][lane]:
+// a lane only ever touches its own column, so every warp-wide atomicAdd is bank-conflict-free and
+// never hits one address twice (the two things that serialise a plain [pass][digit] histogram).
+constexpr int kHistThreads = 1024;
+constexpr int kHistSmemBytes = kSortPasses * kRadix * 32 * 4;   // 128 KB
+
+__global__ void __launch_bounds__(kHistThreads, 1) k_histogram(const uint32_t* __restrict__ keys, uint64_t n,
+                                                               uint32_t* __restrict__ hist /* [4][256], zeroed */) {
+    extern __shared__ uint32_t s_cnt[];                          // [4][256][32]
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    for (int i = tid; i < kSortPasses * kRadix * 32; i += kHistThreads) s_cnt[i] = 0;
     __syncthreads();
 
+    uint32_t* col = s_cnt + lane;
     auto count = [&](uint32_t k) {
-        atomicAdd(&s_hist[0 * kRadix + (k & 255u)], 1u);
-        atomicAdd(&s_hist[1 * kRadix + ((k >> 8) & 255u)], 1u);
-        atomicAdd(&s_hist[2 * kRadix + ((k >> 16) & 255u)], 1u);
-        atomicAdd(&s_hist[3 * kRadix + (k >> 24)], 1u);
+        atomicAdd(col + ((0 * kRadix + (k & 255u)) << 5), 1u);
+        atomicAdd(col + ((1 * kRadix + ((k >> 8) & 255u)) << 5), 1u);
+        atomicAdd(col + ((2 * kRadix + ((k >> 16) & 255u)) << 5), 1u);
+        atomicAdd(col + ((3 * kRadix + (k >> 24)) << 5), 1u);
     };
 
     // scalar head up to 16-byte alignment, 128-bit body, scalar tail
@@ -59,9 +69,18 @@ __global__ void __launch_bounds__(256) k_histogram(const uint32_t* __restrict__ 
     if (head > n) head = n;
     const uint64_t nvec = (n - head) >> 2;
     const uint4* __restrict__ vkeys = reinterpret_cast<const uint4*>(keys + head);
-    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t v = gtid; v < nvec; v += gstride) {
+    const uint64_t gtid = (uint64_t)blockIdx.x * kHistThreads + tid;
+    const uint64_t gstride = (uint64_t)gridDim.x * kHistThreads;
+    uint64_t v = gtid;
+    for (; v + 3 * gstride < nvec; v += 4 * gstride) {           // 4 independent 128-bit loads in flight
+        const uint4 q0 = __ldg(vkeys + v), q1 = __ldg(vkeys + v + gstride);
+        const uint4 q2 = __ldg(vkeys + v + 2 * gstride), q3 = __ldg(vkeys + v + 3 * gstride);
+        count(q0.x); count(q0.y); count(q0.z); count(q0.w);
+        count(q1.x); count(q1.y); count(q1.z); count(q1.w);
+        count(q2.x); count(q2.y); count(q2.z); count(q2.w);
+        count(q3.x); count(q3.y); count(q3.z); count(q3.w);
+    }
+    for (; v < nvec; v += gstride) {
         const uint4 q = __ldg(vkeys + v);
         count(q.x); count(q.y); count(q.z); count(q.w);
     }
@@ -69,10 +88,12 @@ __global__ void __launch_bounds__(256) k_histogram(const uint32_t* __restrict__ 
     const uint64_t tail0 = head + (nvec << 2);
     if (tail0 + gtid < n) count(keys[tail0 + gtid]);
     __syncthreads();
-    for (int i = threadIdx.x; i < kSortPasses * kRadix; i += blockDim.x) {
-        const uint32_t c = s_hist[i];
-        if (c) atomicAdd(&hist[i], c);
-    }
+
+    // thread t folds the 32 lane columns of bin t (rotated start => conflict-free) and publishes it
+    uint32_t sum = 0;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) sum += s_cnt[(tid << 5) + ((l + lane) & 31u)];
+    if (sum) atomicAdd(&hist[tid], sum);
 }
 
 // exclusive scan of each pass's 256 counts -> first output position of every digit (in place).
@@ -98,33 +119,55 @@ __global__ void __launch_bounds__(kSortPasses * kRadix) k_scan_histogram(uint32_
 }
 
 // ---- one radix pass: rank + look-back + staged stable scatter ------------------------------------
+// Shared memory per CTA (dynamic, 50.6 KB => 4 CTAs per SM):
+//   s_match [8 warps][256] x {mask, count}  16 KB   per-warp digit words (see ranking below); after
+//                                                   ranking, count is rewritten to the warp's base slot
+//   s_pairs [4096] x {key, value}           32 KB   the tile staged in digit order
+//   s_global_off[256], s_scan[8], s_tile_id
+//
+// Ranking ("which lanes of my warp hold my digit, and how many did earlier rounds of this warp
+// hold") replaces the HLSL WavePrefixCountBits/WavePrefixSum splits of LocalRadixSort.compute:29-91.
+// Each lane ORs its lane bit into word[digit].mask with one shared-memory atomic; after a warp sync
+// every lane reads the 64-bit word back: mask = this round's peers, count = peers of all earlier
+// rounds. The lowest peer lane then writes {0, count + popc(mask)} -- clearing the mask and
+// advancing the running count in one store. Measured on B200 this costs ~7 SM-cycles per warp-round
+// against ~25 for an 8-ballot match and ~60 for match.any (tools/micro/match_bench.cu).
+constexpr int kMatchBytes = kWarps * kRadix * 8;
+template <bool kHasValues> struct PassSmem {
+    static constexpr int kPairBytes = kTile * (kHasValues ? 8 : 4);
+    static constexpr int kTotal = kMatchBytes + kPairBytes + kRadix * 4 + kWarps * 4 + 16;
+};
+
 template <typename StatusT, bool kHasValues>
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, kCtasPerSM)
 k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ digit_base /* [256] */,
            uint32_t* __restrict__ tile_counter, StatusT* __restrict__ status /* [tiles][256], zeroed */) {
     using ST = StatusTraits<StatusT>;
-    __shared__ uint32_t s_warp_hist[kWarps][kRadix];   // per-warp digit counts, then exclusive warp offsets
-    __shared__ uint32_t s_keys[kTile];
-    __shared__ uint32_t s_vals[kHasValues ? kTile : 1];
-    __shared__ uint32_t s_tile_start[kRadix];          // first tile-local slot of each digit
-    __shared__ uint32_t s_global_off[kRadix];          // global position of slot 0 of each digit's run, minus tile_start
-    __shared__ uint32_t s_scan[kWarps];
-    __shared__ uint32_t s_tile_id;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint2* s_match = reinterpret_cast<uint2*>(smem);                              // [kWarps][256]
+    uint2* s_pairs = reinterpret_cast<uint2*>(smem + kMatchBytes);                // kHasValues
+    uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem + kMatchBytes);           // !kHasValues
+    uint32_t* s_global_off = reinterpret_cast<uint32_t*>(smem + kMatchBytes + PassSmem<kHasValues>::kPairBytes);
+    uint32_t* s_scan = s_global_off + kRadix;
+    uint32_t* s_tile_id = s_scan + kWarps;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     // dynamic tile id: a tile only ever waits on tiles that already started => forward progress
-    if (tid == 0) s_tile_id = atomicAdd(tile_counter, 1u);
+    if (tid == 0) *s_tile_id = atomicAdd(tile_counter, 1u);
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem);
 #pragma unroll
-    for (int i = tid; i < kWarps * kRadix; i += kBlock) (&s_warp_hist[0][0])[i] = 0;
+        for (int i = 0; i < kMatchBytes / 16 / kBlock; ++i) z[tid + i * kBlock] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
-    const uint32_t tile = s_tile_id;
+    const uint32_t tile = *s_tile_id;
     const uint32_t tile_base = tile * (uint32_t)kTile;
     const uint32_t valid = min((uint32_t)kTile, n - tile_base);
 
     // warp-striped load: consecutive lanes read consecutive keys (one 128-B line per warp request);
-    // item order (i, lane) is the original order, which the ranking below preserves.
+    // item order (round i, lane) is the original order, which the ranking below preserves.
     const uint32_t warp_first = warp * (32u * kIPT);
     uint32_t key[kIPT];
 #pragma unroll
@@ -132,6 +175,37 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
         const uint32_t idx = warp_first + (uint32_t)i * 32u + lane;
         key[i] = idx < valid ? __ldg(keys_in + tile_base + idx) : 0xFFFFFFFFu;   // tail pads sort last, never stored
     }
+
+    // stable rank of every key among the keys of its warp with the same digit (< 512: two per register)
+    uint32_t rank2[kIPT / 2];
+    const uint32_t lt = lanemask_lt();
+    const uint32_t lane_bit = 1u << lane;
+    uint2* my_match = s_match + warp * kRadix;
+    uint32_t* my_words = reinterpret_cast<uint32_t*>(my_match);
+    // Word d is the 8-byte pair my_match[d] = {mask, count}, with the two halves SWAPPED when bit 4 of
+    // d is set: the 32-bit mask of digit d then lives in bank (2d + ((d >> 4) & 1)) mod 32, so the
+    // atomics (and the count/base lookups, which use the other half) spread over all 32 banks.
+#pragma unroll
+    for (int i = 0; i < kIPT; ++i) {
+        const uint32_t d = (key[i] >> shift) & 255u;
+        const uint32_t sel = (d >> 4) & 1u;
+        atomicOr(my_words + 2u * d + sel, lane_bit);
+        __syncwarp();
+        const uint2 w = my_match[d];                     // peers of this round + peers of earlier rounds
+        __syncwarp();
+        const uint32_t mask = sel ? w.y : w.x, prior = sel ? w.x : w.y;
+        const uint32_t before = __popc(mask & lt);
+        if (before == 0) {
+            const uint32_t now = prior + __popc(mask);
+            my_match[d] = sel ? make_uint2(now, 0u) : make_uint2(0u, now);
+        }
+        const uint32_t r = prior + before;
+        if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // values are fetched now, so their latency hides behind the scan and the look-back below
     uint32_t val[kHasValues ? kIPT : 1];
     if (kHasValues) {
 #pragma unroll
@@ -141,71 +215,60 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
         }
     }
 
-    // stable rank of every key among the keys of its warp with the same digit, by warp ballots
-    uint32_t rank[kIPT];
-    const uint32_t lt = lanemask_lt();
-    uint32_t* my_hist = s_warp_hist[warp];
+    // thread d (< 256) owns digit d: tile count, exclusive offsets across warps, look-back
+    const uint32_t d = tid;
+    uint32_t* s_words = reinterpret_cast<uint32_t*>(s_match);
+    const uint32_t cnt_half = 1u - ((d >> 4) & 1u);      // which half of word d holds the count
+    uint32_t count = 0, incl = 0;
+    StatusT* my_status = status + (size_t)tile * kRadix + (d & 255u);
+    if (d < kRadix) {
 #pragma unroll
-    for (int i = 0; i < kIPT; ++i) {
-        const uint32_t d = (key[i] >> shift) & 255u;
-        uint32_t peers = 0xFFFFFFFFu;
-#pragma unroll
-        for (int b = 0; b < kRadixBits; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);
-            peers &= bit ? ballot : ~ballot;
-        }
-        const uint32_t before = __popc(peers & lt);
-        const int leader = __ffs(peers) - 1;
-        uint32_t prior = 0;
-        if (before == 0) {                       // lowest lane holding this digit
-            prior = my_hist[d];
-            my_hist[d] = prior + __popc(peers);
-        }
-        prior = __shfl_sync(0xFFFFFFFFu, prior, leader);
-        rank[i] = prior + before;
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // thread d owns digit d: exclusive offsets across warps, tile count, look-back, tile-local start
-    {
-        const uint32_t d = tid;                  // kBlock == kRadix
-        uint32_t count = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t c = s_warp_hist[w][d];
-            s_warp_hist[w][d] = count;
-            count += c;
-        }
-        StatusT* my_status = status + (size_t)tile * kRadix + d;
+        for (int w = 0; w < kWarps; ++w) count += s_words[(w * kRadix + d) * 2 + cnt_half];
+        // publish this tile's count of digit d as early as possible
         ST::store(my_status, (tile == 0 ? ST::kPrefix : ST::kAggregate) | (StatusT)count);
-
-        // block exclusive scan of the tile counts over digits
-        uint32_t incl = count;
+        incl = count;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
             if (lane >= (uint32_t)o) incl += y;
         }
         if (lane == 31) s_scan[warp] = incl;
-        __syncthreads();
+    }
+    __syncthreads();
+    if (d < kRadix) {
         uint32_t wbase = 0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) wbase += (w < (int)warp) ? s_scan[w] : 0u;
-        const uint32_t tile_start = wbase + incl - count;
-        s_tile_start[d] = tile_start;
+        for (int w = 0; w < kRadix / 32; ++w) wbase += (w < (int)warp) ? s_scan[w] : 0u;
+        const uint32_t tile_start = wbase + incl - count;     // first tile-local slot of digit d
+        // in place: word[w][d].count becomes the first tile slot of warp w's keys of digit d
+        uint32_t running = tile_start;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = s_words[(w * kRadix + d) * 2 + cnt_half];
+            s_words[(w * kRadix + d) * 2 + cnt_half] = running;
+            running += c;
+        }
 
-        // decoupled look-back over the preceding tiles' counts of this digit
+        // decoupled look-back over the preceding tiles' counts of this digit, four tiles per round
+        // trip (the loads are independent; only the accumulation is ordered)
         uint32_t exclusive = 0;
         if (tile > 0) {
-            const StatusT* look = my_status - kRadix;
-            while (true) {
-                StatusT s;
-                do { s = ST::load(look); } while ((s & ST::kFlagMask) == 0);
-                exclusive += (uint32_t)(s & ST::kValueMask);
-                if (s & ST::kPrefix) break;
-                look -= kRadix;
+            int32_t t = (int32_t)tile - 1;
+            bool done = false;
+            while (!done) {
+                StatusT s4[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    s4[k] = (t - k >= 0) ? ST::load(status + (size_t)(t - k) * kRadix + d) : (StatusT)ST::kPrefix;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!done) {
+                        while ((s4[k] & ST::kFlagMask) == 0) s4[k] = ST::load(status + (size_t)(t - k) * kRadix + d);
+                        exclusive += (uint32_t)(s4[k] & ST::kValueMask);
+                        done = (s4[k] & ST::kPrefix) != 0;
+                    }
+                }
+                t -= 4;
             }
             ST::store(my_status, ST::kPrefix | (StatusT)(exclusive + count));
         }
@@ -216,10 +279,10 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     // stage the tile in digit order
 #pragma unroll
     for (int i = 0; i < kIPT; ++i) {
-        const uint32_t d = (key[i] >> shift) & 255u;
-        const uint32_t slot = s_tile_start[d] + my_hist[d] + rank[i];
-        s_keys[slot] = key[i];
-        if (kHasValues) s_vals[slot] = val[i];
+        const uint32_t dg = (key[i] >> shift) & 255u;
+        const uint32_t slot = my_words[2u * dg + 1u - ((dg >> 4) & 1u)] + ((rank2[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu);
+        if (kHasValues) s_pairs[slot] = make_uint2(key[i], val[i]);
+        else s_keys[slot] = key[i];
     }
     __syncthreads();
 
@@ -228,14 +291,24 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     for (int i = 0; i < kIPT; ++i) {
         const uint32_t p = tid + (uint32_t)i * kBlock;
         if (p < valid) {
-            const uint32_t k = s_keys[p];
-            const uint32_t dst = s_global_off[(k >> shift) & 255u] + p;
-            keys_out[dst] = k;
-            if (kHasValues) vals_out[dst] = s_vals[p];
+            if (kHasValues) {
+                const uint2 kv = s_pairs[p];
+                const uint32_t dst = s_global_off[(kv.x >> shift) & 255u] + p;
+                keys_out[dst] = kv.x;
+                vals_out[dst] = kv.y;
+            } else {
+                const uint32_t k = s_keys[p];
+                keys_out[s_global_off[(k >> shift) & 255u] + p] = k;
+            }
         }
     }
 }
 
+inline uint32_t histogram_grid(uint64_t count) {
+    cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes);   // per device, cheap
+    const uint64_t vec_work = (count + 4 * kHistThreads - 1) / (4 * kHistThreads);
+    return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(vec_work, 1), (uint64_t)kNumSMs);
+}
 inline uint32_t num_tiles(uint64_t count) { return (uint32_t)((count + kTile - 1) / kTile); }
 inline bool wide_status(uint64_t count) { return count >= (1ull << 30); }
 inline uint64_t status_words_bytes(uint64_t count) { return (uint64_t)num_tiles(count) * kRadix * (wide_status(count) ? 8 : 4); }
@@ -244,12 +317,15 @@ template <typename StatusT>
 cudaError_t run_pass(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint64_t count, int shift,
                      const uint32_t* digit_base, uint32_t* tile_counter, void* status, cudaStream_t stream) {
     const uint32_t tiles = num_tiles(count);
-    if (vi != nullptr)
-        k_onesweep<StatusT, true><<<tiles, kBlock, 0, stream>>>(ki, vi, ko, vo, (uint32_t)count, shift, digit_base,
-                                                               tile_counter, static_cast<StatusT*>(status));
-    else
-        k_onesweep<StatusT, false><<<tiles, kBlock, 0, stream>>>(ki, vi, ko, vo, (uint32_t)count, shift, digit_base,
-                                                                tile_counter, static_cast<StatusT*>(status));
+    if (vi != nullptr) {
+        cudaFuncSetAttribute(k_onesweep<StatusT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PassSmem<true>::kTotal);
+        k_onesweep<StatusT, true><<<tiles, kBlock, PassSmem<true>::kTotal, stream>>>(
+            ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter, static_cast<StatusT*>(status));
+    } else {
+        cudaFuncSetAttribute(k_onesweep<StatusT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PassSmem<false>::kTotal);
+        k_onesweep<StatusT, false><<<tiles, kBlock, PassSmem<false>::kTotal, stream>>>(
+            ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter, static_cast<StatusT*>(status));
+    }
     return cudaGetLastError();
 }
 
@@ -287,20 +363,20 @@ void sort_scratch_free(SortScratch& s) {
 }
 
 cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt, uint64_t count,
-                       SortScratch& s, cudaStream_t stream, uint64_t* launches) {
+                       SortScratch& s, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events) {
     if (count == 0) return cudaSuccess;
     cudaError_t e;
     if ((e = sort_scratch_reserve(s, count, false)) != cudaSuccess) return e;
     const uint64_t pass_bytes = status_words_bytes(count);
+    if (events && (e = cudaEventRecord(events[0], stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s.hist, 0, kSortPasses * kRadix * 4, stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s.status, 0, kHeaderWords * 4 + kSortPasses * pass_bytes, stream)) != cudaSuccess) return e;
 
-    const uint64_t vec_work = (count + 4 * 256 - 1) / (4 * 256);
-    const uint32_t hgrid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(vec_work, 1), (uint64_t)kNumSMs * 8);
-    k_histogram<<<hgrid, 256, 0, stream>>>(keys, count, s.hist);
+    k_histogram<<<histogram_grid(count), kHistThreads, kHistSmemBytes, stream>>>(keys, count, s.hist);
     k_scan_histogram<<<1, kSortPasses * kRadix, 0, stream>>>(s.hist, nullptr, -1);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (launches) *launches += 2;
+    if (events && (e = cudaEventRecord(events[1], stream)) != cudaSuccess) return e;
 
     uint32_t* counters = static_cast<uint32_t*>(s.status);
     char* status0 = static_cast<char*>(s.status) + kHeaderWords * 4;
@@ -314,6 +390,7 @@ cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint3
             e = run_pass<uint32_t>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream);
         if (e != cudaSuccess) return e;
         if (launches) *launches += 1;
+        if (events && (e = cudaEventRecord(events[2 + pass], stream)) != cudaSuccess) return e;
         const uint32_t* tk = ki; const uint32_t* tv = vi;
         ki = ko; vi = vo;
         ko = const_cast<uint32_t*>(tk); vo = const_cast<uint32_t*>(tv);
@@ -334,9 +411,7 @@ cudaError_t partition_pass(const uint32_t* src_keys, const uint32_t* src_vals, u
     const uint64_t pass_bytes = status_words_bytes(count);
     if ((e = cudaMemsetAsync(s.status, 0, kHeaderWords * 4 + pass_bytes, stream)) != cudaSuccess) return e;
     const int pass = bit_offset / kRadixBits;
-    const uint64_t vec_work = (count + 4 * 256 - 1) / (4 * 256);
-    const uint32_t hgrid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(vec_work, 1), (uint64_t)kNumSMs * 8);
-    k_histogram<<<hgrid, 256, 0, stream>>>(src_keys, count, s.hist);
+    k_histogram<<<histogram_grid(count), kHistThreads, kHistSmemBytes, stream>>>(src_keys, count, s.hist);
     k_scan_histogram<<<1, kSortPasses * kRadix, 0, stream>>>(s.hist, histogram_out, pass);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     uint32_t* counters = static_cast<uint32_t*>(s.status);

@@ -31,8 +31,9 @@ struct SortScratch {
 
 // Launches enqueue on `stream`; every function returns the first CUDA error it saw.
 // K2: stable LSD sort of count pairs, result back in (keys, vals). alt buffers must hold count elements.
+// events (optional, 6): recorded before the histogram, after it, and after each of the 4 passes.
 cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt, uint64_t count,
-                       SortScratch& scratch, cudaStream_t stream, uint64_t* launches);
+                       SortScratch& scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events = nullptr);
 // One stable partition pass src -> dst by digit (key >> bit_offset) & 255.
 cudaError_t partition_pass(const uint32_t* src_keys, const uint32_t* src_vals, uint32_t* dst_keys, uint32_t* dst_vals,
                            uint64_t count, int bit_offset, uint32_t* histogram_out, SortScratch& scratch,

@@ -136,6 +136,11 @@ class Context:
         self._check(self._lib.usrt_last_rebuild_ms(self._h, out))
         return dict(zip(("morton", "sort", "distribute", "tree", "bvh", "total"), [float(x) for x in out]))
 
+    def last_sort_ms(self):
+        out = (ctypes.c_float * 6)()
+        self._check(self._lib.usrt_last_sort_ms(self._h, out))
+        return dict(zip(("histogram", "pass0", "pass8", "pass16", "pass24", "total"), [float(x) for x in out]))
+
     def set_trace_mode(self, mode):
         self._check(self._lib.usrt_set_trace_mode(self._h, int(mode)))
 
