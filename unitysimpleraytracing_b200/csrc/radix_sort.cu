@@ -219,7 +219,7 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     const uint32_t d = tid;
     uint32_t* s_words = reinterpret_cast<uint32_t*>(s_match);
     const uint32_t cnt_half = 1u - ((d >> 4) & 1u);      // which half of word d holds the count
-    uint32_t count = 0, incl = 0;
+    uint32_t count = 0, incl = 0, my_tile_start = 0;
     StatusT* my_status = status + (size_t)tile * kRadix + (d & 255u);
     if (d < kRadix) {
 #pragma unroll
@@ -249,6 +249,22 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
             running += c;
         }
 
+        my_tile_start = tile_start;
+    }
+    __syncthreads();
+
+    // stage the tile in digit order
+#pragma unroll
+    for (int i = 0; i < kIPT; ++i) {
+        const uint32_t dg = (key[i] >> shift) & 255u;
+        const uint32_t slot = my_words[2u * dg + 1u - ((dg >> 4) & 1u)] + ((rank2[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu);
+        if (kHasValues) s_pairs[slot] = make_uint2(key[i], val[i]);
+        else s_keys[slot] = key[i];
+    }
+    // Look-back AFTER staging: the aggregate was published before the scan, so by now the preceding
+    // tiles have usually posted their inclusive prefixes and the walk resolves in one round trip.
+    if (d < kRadix) {
+        const uint32_t tile_start = my_tile_start;
         // decoupled look-back over the preceding tiles' counts of this digit, four tiles per round
         // trip (the loads are independent; only the accumulation is ordered)
         uint32_t exclusive = 0;
@@ -273,16 +289,6 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
             ST::store(my_status, ST::kPrefix | (StatusT)(exclusive + count));
         }
         s_global_off[d] = digit_base[d] + exclusive - tile_start;   // wraps mod 2^32 by design
-    }
-    __syncthreads();
-
-    // stage the tile in digit order
-#pragma unroll
-    for (int i = 0; i < kIPT; ++i) {
-        const uint32_t dg = (key[i] >> shift) & 255u;
-        const uint32_t slot = my_words[2u * dg + 1u - ((dg >> 4) & 1u)] + ((rank2[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu);
-        if (kHasValues) s_pairs[slot] = make_uint2(key[i], val[i]);
-        else s_keys[slot] = key[i];
     }
     __syncthreads();
 
