@@ -133,6 +133,15 @@ int usrt_last_sort_ms(usrt_context* ctx, float out_ms[6]);
  * the device copy stays readable through usrt_hits_device. */
 int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
                        const float camera_to_world[16], int y0, int y1, usrt_raycast_result* host_out);
+/* Ray sharding across GPUs against a replicated BVH (north_star (a)): shard s of S traces the row
+ * blocks b (block = block_rows consecutive rows) with b % S == s -- interleaved for load balance -- in
+ * ONE launch and writes them compactly: local row lr = (b / S) * block_rows + row_in_block, record
+ * index lr * width + x. Every shard's buffer has ceil(ceil(H / block_rows) / S) * block_rows rows
+ * (equal sizes for an all-gather); rows that fall outside the frame are zero-filled. dev_out may be
+ * NULL (the context's hit buffer is used, see usrt_hits_device); host_out may be NULL. */
+int usrt_trace_primary_sharded(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
+                               const float camera_to_world[16], int block_rows, int shard, int num_shards,
+                               void* dev_out, usrt_raycast_result* host_out);
 /* Same traversal for caller rays: 8 floats per ray (origin.xyz, pad, dir.xyz, pad); dir is used as
  * given, inv_dir = 1/dir. */
 int usrt_trace_rays(usrt_context* ctx, const float* host_rays, uint64_t num_rays, usrt_raycast_result* host_out);

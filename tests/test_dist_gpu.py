@@ -1,0 +1,80 @@
+"""The two sharded paths on real GPUs over NCCL (needs >= 2 visible devices; run with gpurun --gpus 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _need_gpus(k):
+    import torch
+    if torch.cuda.device_count() < k:
+        pytest.skip("needs %d GPUs, %d visible" % (k, torch.cuda.device_count()))
+
+
+def _ray_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    from unitysimpleraytracing_b200 import dist as udist, meshes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    tris = meshes.scene_c1()
+    cam = meshes.SCENE_SOUP_CAMERA
+    d = udist.RayShardedDrawer(tris, rank, world).Awake()
+    frame = d.Update(320, 180, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    np.save(os.path.join(out_dir, "frame%d.npy" % rank), frame)
+    d.OnDestroy()
+    dist.destroy_process_group()
+
+
+def test_ray_sharded_frame_matches_oracle(tmp_path, oracle):
+    _need_gpus(2)
+    import torch.multiprocessing as mp
+    from unitysimpleraytracing_b200 import meshes
+    world = 2
+    mp.spawn(_ray_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    cam = meshes.SCENE_SOUP_CAMERA
+    want = oracle.Scene(meshes.scene_c1()).trace_primary(320, 180, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], threads=8)
+    for r in range(world):
+        got = np.load(tmp_path / ("frame%d.npy" % r))
+        assert got.tobytes() == want.tobytes()
+
+
+def _sort_worker(rank, world, port, n, out_dir):
+    import torch
+    import torch.distributed as dist
+    from unitysimpleraytracing_b200 import dist as udist, host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    rng = np.random.default_rng(7 + rank)
+    keys = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    keys[::5] = keys[0]                                   # duplicates across ranks: stability matters
+    vals = (np.arange(n) + rank * n).astype(np.uint32)
+    ctx = host.Context(2, device=rank)
+    k, v = udist.dist_sort_pairs(torch.from_numpy(keys.view(np.int32)).to(dev), torch.from_numpy(vals.view(np.int32)).to(dev), ctx=ctx)
+    torch.cuda.synchronize()
+    np.savez(os.path.join(out_dir, "s%d.npz" % rank), k=k.cpu().numpy().view(np.uint32), v=v.cpu().numpy().view(np.uint32), ik=keys, iv=vals)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_dist_sort_matches_global_stable_sort(tmp_path):
+    _need_gpus(2)
+    import torch.multiprocessing as mp
+    world, n = 2, 1 << 20
+    mp.spawn(_sort_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / ("s%d.npz" % r)) for r in range(world)]
+    all_k = np.concatenate([p["ik"] for p in parts]); all_v = np.concatenate([p["iv"] for p in parts])
+    order = np.argsort(all_k, kind="stable")
+    assert np.array_equal(np.concatenate([p["k"] for p in parts]), all_k[order])
+    assert np.array_equal(np.concatenate([p["v"] for p in parts]), all_v[order])

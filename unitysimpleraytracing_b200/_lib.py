@@ -41,6 +41,8 @@ SIGNATURES = {
     "usrt_last_rebuild_ms": (_c.c_int, [_P, _c.POINTER(_c.c_float)]),
     "usrt_last_sort_ms": (_c.c_int, [_P, _c.POINTER(_c.c_float)]),
     "usrt_trace_primary": (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _P, _c.c_int, _c.c_int, _P]),
+    "usrt_trace_primary_sharded": (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _P, _c.c_int, _c.c_int,
+                                              _c.c_int, _P, _P]),
     "usrt_trace_rays": (_c.c_int, [_P, _P, _c.c_uint64, _P]),
     "usrt_trace_rays_device": (_c.c_int, [_P, _P, _c.c_uint64, _P]),
     "usrt_hits_device": (_c.c_int, [_P, _c.POINTER(_P), _c.POINTER(_c.c_uint64)]),

@@ -453,6 +453,7 @@ int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plan
     p.width = width; p.height = height; p.near_plane = near_plane; p.tan_half_fov = tan_half_fov;
     memcpy(p.m, camera_to_world, sizeof(p.m));
     p.y0 = y0; p.y1 = y1;
+    p.block_rows = 1; p.shard = 0; p.num_shards = 0; p.local_rows = 0;
     TraceScene s{ctx->packed_nodes, ctx->packed_tris, ctx->bvh};
     CU(ctx, launch_trace_primary(s, p, ctx->hits, ctx->trace_mode, ctx->stream));
     ctx->launches += (y1 > y0) ? 1 : 0;
@@ -460,6 +461,42 @@ int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plan
         const size_t off = (size_t)y0 * width;
         CU(ctx, cudaMemcpyAsync(host_out + off, ctx->hits + off, (size_t)(y1 - y0) * width * sizeof(usrt_raycast_result),
                                 cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return USRT_OK;
+}
+
+int usrt_trace_primary_sharded(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
+                               const float camera_to_world[16], int block_rows, int shard, int num_shards,
+                               void* dev_out, usrt_raycast_result* host_out) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_BVH)) return fail(ctx, USRT_ERR_STATE, "trace: BVH not built");
+    if (width <= 0 || height <= 0 || !camera_to_world || block_rows <= 0 || num_shards <= 0 || shard < 0 || shard >= num_shards)
+        return fail(ctx, USRT_ERR_ARG, "trace_primary_sharded: bad frame %dx%d block_rows=%d shard %d/%d", width, height,
+                    block_rows, shard, num_shards);
+    if (int r = bind_device(ctx)) return r;
+    const int blocks_total = (height + block_rows - 1) / block_rows;
+    const int blocks_per_shard = (blocks_total + num_shards - 1) / num_shards;      // padded: equal on every shard
+    const int local_rows = blocks_per_shard * block_rows;
+    const uint64_t count = (uint64_t)local_rows * (uint64_t)width;
+    usrt_raycast_result* out = static_cast<usrt_raycast_result*>(dev_out);
+    if (!out) {
+        if (int r = ensure_hits(ctx, count)) return r;
+        out = ctx->hits;
+        ctx->hits_count = count;
+    }
+    // rows past the frame (padding of the last block / last shard) are never traced: pre-fill with misses
+    CU(ctx, cudaMemsetAsync(out, 0, count * sizeof(usrt_raycast_result), ctx->stream));
+    PrimaryParams p;
+    p.width = width; p.height = height; p.near_plane = near_plane; p.tan_half_fov = tan_half_fov;
+    memcpy(p.m, camera_to_world, sizeof(p.m));
+    p.y0 = 0; p.y1 = 0;
+    p.block_rows = block_rows; p.shard = shard; p.num_shards = num_shards; p.local_rows = local_rows;
+    TraceScene s{ctx->packed_nodes, ctx->packed_tris, ctx->bvh};
+    CU(ctx, launch_trace_primary(s, p, out, ctx->trace_mode, ctx->stream));
+    ctx->launches += 1;
+    if (host_out) {
+        CU(ctx, cudaMemcpyAsync(host_out, out, count * sizeof(usrt_raycast_result), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return USRT_OK;

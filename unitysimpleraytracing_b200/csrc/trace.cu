@@ -169,11 +169,23 @@ template <bool kCulled>
 __global__ void __launch_bounds__(128) k_trace_primary(TraceScene scene, PrimaryParams p, usrt_raycast_result* __restrict__ out) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t x = blockIdx.x * kTileW + (warp & 1u) * 8u + (lane & 7u);
-    const uint32_t y = (uint32_t)p.y0 + blockIdx.y * kTileH + (warp >> 1) * 4u + (lane >> 3);
-    if (x >= (uint32_t)p.width || y >= (uint32_t)p.y1) return;
+    const uint32_t row = blockIdx.y * kTileH + (warp >> 1) * 4u + (lane >> 3);
+    uint32_t y, out_row;
+    if (p.num_shards > 0) {                                            // ray sharding: interleaved row blocks
+        if (row >= (uint32_t)p.local_rows) return;
+        const uint32_t blk = row / (uint32_t)p.block_rows, in_blk = row % (uint32_t)p.block_rows;
+        y = (blk * (uint32_t)p.num_shards + (uint32_t)p.shard) * (uint32_t)p.block_rows + in_blk;
+        out_row = row;
+        if (y >= (uint32_t)p.height) return;
+    } else {
+        y = (uint32_t)p.y0 + row;
+        out_row = y;
+        if (y >= (uint32_t)p.y1) return;
+    }
+    if (x >= (uint32_t)p.width) return;
     const Ray ray = primary_ray(p, x, y);
     const usrt_raycast_result h = traverse<kCulled>(scene, ray);
-    store_hit(out, (size_t)y * (size_t)p.width + x, h);                // hit record index = y*W + x
+    store_hit(out, (size_t)out_row * (size_t)p.width + x, h);          // frame mode: record index = y*W + x
 }
 
 template <bool kCulled>
@@ -194,8 +206,9 @@ __global__ void __launch_bounds__(128) k_trace_rays(TraceScene scene, const floa
 
 cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p, usrt_raycast_result* out, int mode,
                                  cudaStream_t stream) {
-    if (p.y1 <= p.y0 || p.width <= 0) return cudaSuccess;
-    const dim3 grid((p.width + kTileW - 1) / kTileW, (p.y1 - p.y0 + kTileH - 1) / kTileH);
+    const int rows = p.num_shards > 0 ? p.local_rows : p.y1 - p.y0;
+    if (rows <= 0 || p.width <= 0) return cudaSuccess;
+    const dim3 grid((p.width + kTileW - 1) / kTileW, (rows + kTileH - 1) / kTileH);
     if (mode == 1) k_trace_primary<true><<<grid, 128, 0, stream>>>(scene, p, out);
     else k_trace_primary<false><<<grid, 128, 0, stream>>>(scene, p, out);
     return cudaGetLastError();

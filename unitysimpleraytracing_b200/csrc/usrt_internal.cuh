@@ -70,7 +70,11 @@ struct PrimaryParams {
     int width, height;
     float near_plane, tan_half_fov;
     float m[16];                  // row-major cameraToWorld
-    int y0, y1;
+    int y0, y1;                   // frame mode: rows [y0, y1), record index y*width + x
+    // sharded mode (num_shards > 0): this shard owns the row blocks b with b % num_shards == shard,
+    // block = block_rows consecutive rows; local row lr <-> frame row
+    // ((lr / block_rows) * num_shards + shard) * block_rows + lr % block_rows; record index lr*width + x
+    int block_rows, shard, num_shards, local_rows;
 };
 cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p, usrt_raycast_result* out, int mode,
                                  cudaStream_t stream);

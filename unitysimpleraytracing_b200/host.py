@@ -74,6 +74,15 @@ class Context:
     def set_stream(self, cuda_stream):
         self._check(self._lib.usrt_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
 
+    def use_torch_stream(self, stream=None):
+        """Enqueue on a torch CUDA stream (default: torch's current stream on this device). torch's
+        default stream has handle 0, which the ABI reads as "back to the context's own stream", so it is
+        passed as cudaStreamLegacy (0x1) instead."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        self.set_stream(stream.cuda_stream or 1)
+
     def set_world_bounds(self, whole_min, whole_max):
         self._check(self._lib.usrt_set_world_bounds(self._h, whole_min, whole_max))
 
@@ -151,6 +160,18 @@ class Context:
             out = np.zeros(width * height, RaycastResult)
         self._check(self._lib.usrt_trace_primary(self._h, width, height, float(near), float(tan_half_fov), _ptr(m),
                                                  y0, y1, _ptr(out) if download else None))
+        return out
+
+    def trace_primary_sharded(self, width, height, near, tan_half_fov, cam_to_world, block_rows, shard, num_shards,
+                              dev_out=None, download=False):
+        """One launch over this shard's interleaved row blocks; compact output (see include/usrt.h)."""
+        m = np.ascontiguousarray(cam_to_world, np.float32).reshape(16)
+        blocks = -(-height // block_rows)
+        local_rows = -(-blocks // num_shards) * block_rows
+        out = np.zeros(local_rows * width, RaycastResult) if download else None
+        self._check(self._lib.usrt_trace_primary_sharded(self._h, width, height, float(near), float(tan_half_fov),
+                                                         _ptr(m), block_rows, shard, num_shards,
+                                                         ctypes.c_void_p(dev_out) if dev_out else None, _ptr(out)))
         return out
 
     def trace_rays(self, rays, out=None):
