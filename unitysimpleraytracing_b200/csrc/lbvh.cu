@@ -232,10 +232,11 @@ __global__ void __launch_bounds__(256) k_construct_bvh(uint32_t n, const uint32_
         // :184-189 -- first arrival leaves, second arrival merges. XOR instead of CAS(0->1): same
         // first/second decision, and the counter is back to 0 afterwards (re-runnable; the reference
         // zeroes it only once, BVHConstructor.cs:41).
-        __threadfence();                                               // publish our box before the counter RMW
-        const uint32_t old = atomicXor(counters + parent, 1u);
+        // One acq_rel RMW at gpu scope: releases our box store (made below on the previous level)
+        // before the counter flips, and orders the sibling-box loads after it.
+        uint32_t old;
+        asm volatile("atom.acq_rel.gpu.global.xor.b32 %0, [%1], 1;" : "=r"(old) : "l"(counters + parent) : "memory");
         if (old == 0) break;
-        __threadfence();
 
         const uint32_t* node = reinterpret_cast<const uint32_t*>(internal + parent);
         const uint2 l = __ldg(reinterpret_cast<const uint2*>(node + 0));   // leftNode, leftNodeType

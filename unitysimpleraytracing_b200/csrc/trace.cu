@@ -92,11 +92,14 @@ __device__ __forceinline__ usrt_raycast_result traverse(const TraceScene& s, con
         if (!ray_box(rmin.x, rmin.y, rmin.z, rmax.x, rmax.y, rmax.z, ray, &entry)) return best;
     }
 
+    // The reference pushes left then right and pops right first (:148-175). Equivalent walk with the
+    // current node in a register: continue straight into the right child when it is an internal hit,
+    // deferring the left one on the stack; only the deferred siblings ever touch the stack (<= tree
+    // depth <= 33 entries, because DistributeKeys makes the 32-bit keys unique).
     uint32_t stack[64];                                // :133
     int sp = 0;
-    stack[sp++] = 0;
-    while (sp != 0) {
-        const uint32_t index = stack[--sp];
+    uint32_t index = 0;
+    while (true) {
         const float4* pn = s.packed_nodes + (size_t)index * 4;
         const float4 q0 = __ldg(pn + 0), q1 = __ldg(pn + 1), q2 = __ldg(pn + 2), q3 = __ldg(pn + 3);
         const uint32_t lref = __float_as_uint(q3.x), rref = __float_as_uint(q3.y);
@@ -104,29 +107,27 @@ __device__ __forceinline__ usrt_raycast_result traverse(const TraceScene& s, con
         float lentry, rentry;
         bool lhit = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ray, &lentry);
         bool rhit = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ray, &rentry);
-        if (kCulled) {
-            lhit = lhit && !(lentry > best.distance);
+        if (kCulled) lhit = lhit && !(lentry > best.distance);
+        // left child (:148-160): a leaf is tested now, an internal node is visited later
+        if (lhit && (lref & 0x80000000u)) {
+            const float4* t = s.packed_tris + (size_t)(lref & 0x7FFFFFFFu) * 3;
+            ray_triangle(ray, __ldg(t + 0), __ldg(t + 1), __ldg(t + 2), best);
         }
-        // left child (:148-160)
-        if (lhit) {
-            if (lref & 0x80000000u) {
-                const float4* t = s.packed_tris + (size_t)(lref & 0x7FFFFFFFu) * 3;
-                ray_triangle(ray, __ldg(t + 0), __ldg(t + 1), __ldg(t + 2), best);
-            } else {
-                stack[sp++] = lref;
-            }
-        }
-        if (kCulled) {
-            rhit = rhit && !(rentry > best.distance);
-        }
+        if (kCulled) rhit = rhit && !(rentry > best.distance);
         // right child (:162-175)
-        if (rhit) {
-            if (rref & 0x80000000u) {
-                const float4* t = s.packed_tris + (size_t)(rref & 0x7FFFFFFFu) * 3;
-                ray_triangle(ray, __ldg(t + 0), __ldg(t + 1), __ldg(t + 2), best);
-            } else {
-                stack[sp++] = rref;
-            }
+        if (rhit && (rref & 0x80000000u)) {
+            const float4* t = s.packed_tris + (size_t)(rref & 0x7FFFFFFFu) * 3;
+            ray_triangle(ray, __ldg(t + 0), __ldg(t + 1), __ldg(t + 2), best);
+        }
+        const bool lgo = lhit && !(lref & 0x80000000u), rgo = rhit && !(rref & 0x80000000u);
+        if (rgo) {
+            if (lgo) stack[sp++] = lref;
+            index = rref;
+        } else if (lgo) {
+            index = lref;
+        } else {
+            if (sp == 0) break;
+            index = stack[--sp];
         }
     }
     return best;
