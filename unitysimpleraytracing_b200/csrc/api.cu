@@ -35,6 +35,7 @@ struct usrt_context {
     usrt_internal_node* internal = nullptr;
     // BVHConstructor.cs:16 _atomics
     uint32_t* counters = nullptr;
+    uint32_t *up_internal = nullptr, *up_leaf = nullptr;   // K4 -> K5 parent links (side + locality bits)
     // traversal-side arrays written by K5
     float4* packed_nodes = nullptr;
     float4* packed_tris = nullptr;
@@ -151,15 +152,15 @@ int do_distribute(usrt_context* ctx) {
 }
 
 int do_tree(usrt_context* ctx) {
-    CU(ctx, launch_construct_tree(ctx->keys, ctx->n, ctx->internal, ctx->leaf, ctx->stream));
+    CU(ctx, launch_construct_tree(ctx->keys, ctx->n, ctx->internal, ctx->leaf, ctx->up_internal, ctx->up_leaf, ctx->stream));
     ctx->launches += 1;
     ctx->stage |= ST_TREE;
     return USRT_OK;
 }
 
 int do_bvh(usrt_context* ctx) {
-    CU(ctx, launch_construct_bvh(ctx->n, ctx->tri_index, ctx->tri_aabb, ctx->triangles, ctx->internal, ctx->leaf,
-                                 ctx->bvh, ctx->counters, ctx->packed_nodes, ctx->packed_tris, ctx->stream));
+    CU(ctx, launch_construct_bvh(ctx->n, ctx->tri_index, ctx->tri_aabb, ctx->triangles, ctx->internal, ctx->up_internal,
+                                 ctx->up_leaf, ctx->bvh, ctx->counters, ctx->packed_nodes, ctx->packed_tris, ctx->stream));
     ctx->launches += 1;
     ctx->stage |= ST_BVH;
     return USRT_OK;
@@ -172,7 +173,7 @@ extern "C" {
 const char* usrt_version(void) { return "usrt_b200 0.1 (sm_100a)"; }
 
 int usrt_create(int device, uint32_t capacity, usrt_context** out) {
-    if (!out || capacity < 2 || capacity > 0x7FFFFFFFu) return USRT_ERR_ARG;
+    if (!out || capacity < 2 || capacity > (1u << 30)) return USRT_ERR_ARG;   // 30-bit node links
     *out = nullptr;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -197,6 +198,8 @@ int usrt_create(int device, uint32_t capacity, usrt_context** out) {
         CU(ctx, cudaMalloc(&ctx->leaf, c * sizeof(usrt_leaf_node)));
         CU(ctx, cudaMalloc(&ctx->internal, c * sizeof(usrt_internal_node)));
         CU(ctx, cudaMalloc(&ctx->counters, c * 4));
+        CU(ctx, cudaMalloc(&ctx->up_internal, c * 4));
+        CU(ctx, cudaMalloc(&ctx->up_leaf, c * 4));
         CU(ctx, cudaMalloc(&ctx->packed_nodes, c * 4 * sizeof(float4)));
         CU(ctx, cudaMalloc(&ctx->packed_tris, c * 3 * sizeof(float4)));
         CU(ctx, cudaMalloc(&ctx->scan_status, distribute_status_bytes(capacity)));
@@ -225,7 +228,7 @@ int usrt_destroy(usrt_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     void* ptrs[] = {ctx->keys, ctx->keys_alt, ctx->tri_index, ctx->tri_index_alt, ctx->triangles, ctx->tri_aabb,
-                    ctx->bvh, ctx->leaf, ctx->internal, ctx->counters, ctx->packed_nodes, ctx->packed_tris,
+                    ctx->bvh, ctx->leaf, ctx->internal, ctx->counters, ctx->up_internal, ctx->up_leaf, ctx->packed_nodes, ctx->packed_tris,
                     ctx->scan_status, ctx->small, ctx->hits, ctx->rays};
     for (void* p : ptrs)
         if (p) cudaFree(p);

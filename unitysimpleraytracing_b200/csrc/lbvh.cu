@@ -139,9 +139,17 @@ struct KeyView {
     }
 };
 
+// Besides the reference's node arrays, K4 emits one private 32-bit "up link" per node for K5:
+//   bits 0..29 parent index | bit 30 = this node is its parent's RIGHT child | bit 31 = the parent's
+//   whole leaf range lies inside one kRefitBlock-aligned block of leaves (K5 merges it in shared memory).
+constexpr int kRefitBlock = 512;                 // leaves per K5 CTA
+constexpr uint32_t kUpRight = 1u << 30, kUpLocal = 1u << 31, kUpParentMask = (1u << 30) - 1;
+
 __global__ void __launch_bounds__(256) k_construct_tree(const uint32_t* __restrict__ codes, uint32_t n,
                                                         usrt_internal_node* __restrict__ internal,
-                                                        usrt_leaf_node* __restrict__ leaf) {
+                                                        usrt_leaf_node* __restrict__ leaf,
+                                                        uint32_t* __restrict__ up_internal,
+                                                        uint32_t* __restrict__ up_leaf) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;                                            // BVH.compute:101
     const KeyView kv{codes, (int)n};
@@ -194,6 +202,11 @@ __global__ void __launch_bounds__(256) k_construct_tree(const uint32_t* __restri
     else internal[left].parent = i;
     if (right_leaf) *reinterpret_cast<uint2*>(leaf + right) = make_uint2(i, right);
     else internal[right].parent = i;
+
+    const uint32_t link = i | (((uint32_t)first / kRefitBlock == (uint32_t)last / kRefitBlock) ? kUpLocal : 0u);
+    (left_leaf ? up_leaf : up_internal)[left] = link;
+    (right_leaf ? up_leaf : up_internal)[right] = link | kUpRight;
+    if (i == 0) up_internal[0] = USRT_NULL;                            // the root (always node 0) has no parent
 }
 
 // =================================================================================================
@@ -202,14 +215,28 @@ __global__ void __launch_bounds__(256) k_construct_tree(const uint32_t* __restri
 __device__ __forceinline__ float sel_min(float a, float b) { return a < b ? a : b; }
 __device__ __forceinline__ float sel_max(float a, float b) { return a > b ? a : b; }
 
-__global__ void __launch_bounds__(256) k_construct_bvh(uint32_t n, const uint32_t* __restrict__ sorted_indices,
-                                                       const float4* __restrict__ tri_aabb,
-                                                       const float4* __restrict__ tris,
-                                                       const usrt_internal_node* __restrict__ internal,
-                                                       const usrt_leaf_node* __restrict__ leaf,
-                                                       float4* bvh, uint32_t* counters, float4* packed_nodes,
-                                                       float4* __restrict__ packed_tris) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+// One CTA owns kRefitBlock consecutive leaves. A node whose leaf range lies inside the block is
+// "local": its two arrivals meet in shared memory -- each child deposits {box, ref} in its own slot,
+// bumps a shared-memory counter, and the second arrival merges -- so ~99 % of the n-1 merges need
+// no global atomic, no gpu-scope fence and no global re-read of the sibling box. Nodes spanning
+// blocks use the reference's global protocol (BVH.compute:184-215): counter RMW, first arrival
+// leaves, second loads the sibling box and merges.
+__global__ void __launch_bounds__(kRefitBlock) k_construct_bvh(uint32_t n, const uint32_t* __restrict__ sorted_indices,
+                                                               const float4* __restrict__ tri_aabb,
+                                                               const float4* __restrict__ tris,
+                                                               const usrt_internal_node* __restrict__ internal,
+                                                               const uint32_t* __restrict__ up_internal,
+                                                               const uint32_t* __restrict__ up_leaf,
+                                                               float4* bvh, uint32_t* counters, float4* packed_nodes,
+                                                               float4* __restrict__ packed_tris) {
+    __shared__ float4 s_slot[kRefitBlock][2][2];                       // [local node][side]{min|ref, max}
+    __shared__ uint32_t s_count[kRefitBlock];
+    __shared__ uint32_t s_up[kRefitBlock];                             // parent links of the block's internal nodes
+    const uint32_t block_first = blockIdx.x * kRefitBlock;
+    const uint32_t j = block_first + threadIdx.x;
+    s_count[threadIdx.x] = 0;
+    s_up[threadIdx.x] = (j + 1 < n) ? __ldg(up_internal + j) : USRT_NULL;   // local node ids lie in the block's range
+    __syncthreads();
     if (j >= n) return;                                                // BVH.compute:179
 
     const uint32_t tri = __ldg(sorted_indices + j);
@@ -225,42 +252,56 @@ __global__ void __launch_bounds__(256) k_construct_bvh(uint32_t n, const uint32_
         packed_tris[(size_t)j * 3 + 2] = c;
     }
 
-    uint32_t cur = j, cur_ref = 0x80000000u | j;                       // ref: leaf => bit 31 | sorted position
-    bool cur_is_leaf = true;
-    uint32_t parent = __ldg(&leaf[j].parent);                          // BVH.compute:181
-    while (parent != USRT_NULL) {                                      // :182
-        // :184-189 -- first arrival leaves, second arrival merges. XOR instead of CAS(0->1): same
-        // first/second decision, and the counter is back to 0 afterwards (re-runnable; the reference
-        // zeroes it only once, BVHConstructor.cs:41).
-        // One acq_rel RMW at gpu scope: releases our box store (made below on the previous level)
-        // before the counter flips, and orders the sibling-box loads after it.
-        uint32_t old;
-        asm volatile("atom.acq_rel.gpu.global.xor.b32 %0, [%1], 1;" : "=r"(old) : "l"(counters + parent) : "memory");
-        if (old == 0) break;
-
-        const uint32_t* node = reinterpret_cast<const uint32_t*>(internal + parent);
-        const uint2 l = __ldg(reinterpret_cast<const uint2*>(node + 0));   // leftNode, leftNodeType
-        const uint2 r = __ldg(reinterpret_cast<const uint2*>(node + 2));   // rightNode, rightNodeType
-        const uint32_t grand = __ldg(node + 4);
-        const bool i_am_left = (l.x == cur) && ((l.y == USRT_LEAF_NODE) == cur_is_leaf);
-        const uint2 sib = i_am_left ? r : l;
-
-        // sibling box: written by another thread of this launch => read through L2 (.cg), never L1
+    uint32_t cur_ref = 0x80000000u | j;                                // ref: leaf => bit 31 | sorted position
+    uint32_t link = __ldg(up_leaf + j);                                // BVH.compute:181
+    while (link != USRT_NULL) {                                        // :182
+        const uint32_t parent = link & kUpParentMask;
+        const uint32_t side = (link >> 30) & 1u;                       // 0 = we are the left child
         float4 smin, smax;
-        uint32_t sib_ref;
-        if (sib.y == USRT_INTERNAL_NODE) {                             // :197-213
-            smin = __ldcg(bvh + (size_t)sib.x * 2);
-            smax = __ldcg(bvh + (size_t)sib.x * 2 + 1);
-            sib_ref = sib.x;
+        uint32_t sib_ref, next_link;
+        if (link & kUpLocal) {
+            const uint32_t lp = parent - block_first;
+            next_link = s_up[lp];                                      // a local node's id is inside the block
+            s_slot[lp][side][0] = make_float4(bmin.x, bmin.y, bmin.z, __uint_as_float(cur_ref));
+            s_slot[lp][side][1] = bmax;
+            __threadfence_block();
+            const uint32_t old = atomicAdd(&s_count[lp], 1u);          // :184-189 first arrival leaves
+            if (old == 0) break;
+            __threadfence_block();
+            smin = s_slot[lp][side ^ 1u][0];
+            smax = s_slot[lp][side ^ 1u][1];
+            sib_ref = __float_as_uint(smin.w);
         } else {
-            const uint32_t stri = __ldg(sorted_indices + sib.x);
-            smin = __ldg(tri_aabb + (size_t)stri * 2);
-            smax = __ldg(tri_aabb + (size_t)stri * 2 + 1);
-            sib_ref = 0x80000000u | sib.x;
+            // Everything that does not depend on the counter is requested first, so that per level the
+            // serial chain is only: store ack -> counter RMW -> sibling box. (The top ~30 levels of the
+            // tree span blocks and are walked one after the other; their latency is the kernel's.)
+            next_link = __ldg(up_internal + parent);
+            const uint32_t* node = reinterpret_cast<const uint32_t*>(internal + parent);
+            const uint2 sib = __ldg(reinterpret_cast<const uint2*>(node + (side ? 0 : 2)));   // the other child
+            if (sib.y != USRT_INTERNAL_NODE) {                         // leaf sibling: read-only inputs
+                const uint32_t stri = __ldg(sorted_indices + sib.x);
+                smin = __ldg(tri_aabb + (size_t)stri * 2);
+                smax = __ldg(tri_aabb + (size_t)stri * 2 + 1);
+                sib_ref = 0x80000000u | sib.x;
+            }
+            // XOR instead of CAS(0->1): same first/second decision and the counter is back to 0
+            // afterwards (re-runnable; the reference zeroes it once, BVHConstructor.cs:41). Release at
+            // gpu scope publishes our box store of the previous level before the counter flips. The
+            // acquire side is the control dependency on `old` plus ld.global.cg below: the sibling box
+            // is read from L2 (the coherence point) after the RMW returned, so no L1 line can be stale
+            // and the L1-wide invalidate an acquire would cost (CCTL.IVALL) is not needed.
+            uint32_t old;
+            asm volatile("atom.release.gpu.global.xor.b32 %0, [%1], 1;" : "=r"(old) : "l"(counters + parent) : "memory");
+            if (old == 0) break;
+            if (sib.y == USRT_INTERNAL_NODE) {                         // :197-213; written this launch => .cg
+                smin = __ldcg(bvh + (size_t)sib.x * 2);
+                smax = __ldcg(bvh + (size_t)sib.x * 2 + 1);
+                sib_ref = sib.x;
+            }
         }
-        const float4 lmin = i_am_left ? bmin : smin, lmax = i_am_left ? bmax : smax;
-        const float4 rmin = i_am_left ? smin : bmin, rmax = i_am_left ? smax : bmax;
-        const uint32_t lref = i_am_left ? cur_ref : sib_ref, rref = i_am_left ? sib_ref : cur_ref;
+        const float4 lmin = side ? smin : bmin, lmax = side ? smax : bmax;
+        const float4 rmin = side ? bmin : smin, rmax = side ? bmax : smax;
+        const uint32_t lref = side ? sib_ref : cur_ref, rref = side ? cur_ref : sib_ref;
 
         // MergeAABB (:152-170), pads = 0
         bmin = make_float4(sel_min(lmin.x, rmin.x), sel_min(lmin.y, rmin.y), sel_min(lmin.z, rmin.z), 0.0f);
@@ -275,8 +316,8 @@ __global__ void __launch_bounds__(256) k_construct_bvh(uint32_t n, const uint32_
         pn[2] = make_float4(rmin.z, rmax.x, rmax.y, rmax.z);
         pn[3] = make_float4(__uint_as_float(lref), __uint_as_float(rref), 0.0f, 0.0f);
 
-        cur = parent; cur_ref = parent; cur_is_leaf = false;
-        parent = grand;                                                // :217
+        cur_ref = parent;
+        link = next_link;                                              // :217
     }
 }
 
@@ -307,20 +348,19 @@ cudaError_t launch_distribute_keys(const uint32_t* src, uint32_t* dst, uint32_t 
 }
 
 cudaError_t launch_construct_tree(const uint32_t* keys, uint32_t n, usrt_internal_node* internal,
-                                  usrt_leaf_node* leaf, cudaStream_t stream) {
+                                  usrt_leaf_node* leaf, uint32_t* up_internal, uint32_t* up_leaf, cudaStream_t stream) {
     const uint32_t threads = n - 1;
-    k_construct_tree<<<(threads + 255) / 256, 256, 0, stream>>>(keys, n, internal, leaf);
+    k_construct_tree<<<(threads + 255) / 256, 256, 0, stream>>>(keys, n, internal, leaf, up_internal, up_leaf);
     return cudaGetLastError();
 }
 
 cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
                                  const usrt_triangle* tris, const usrt_internal_node* internal,
-                                 const usrt_leaf_node* leaf, usrt_aabb* bvh, uint32_t* counters, float4* packed_nodes,
-                                 float4* packed_tris, cudaStream_t stream) {
-    k_construct_bvh<<<(n + 255) / 256, 256, 0, stream>>>(n, sorted_indices, reinterpret_cast<const float4*>(tri_aabb),
-                                                         reinterpret_cast<const float4*>(tris), internal, leaf,
-                                                         reinterpret_cast<float4*>(bvh), counters, packed_nodes,
-                                                         packed_tris);
+                                 const uint32_t* up_internal, const uint32_t* up_leaf, usrt_aabb* bvh, uint32_t* counters,
+                                 float4* packed_nodes, float4* packed_tris, cudaStream_t stream) {
+    k_construct_bvh<<<(n + kRefitBlock - 1) / kRefitBlock, kRefitBlock, 0, stream>>>(
+        n, sorted_indices, reinterpret_cast<const float4*>(tri_aabb), reinterpret_cast<const float4*>(tris), internal,
+        up_internal, up_leaf, reinterpret_cast<float4*>(bvh), counters, packed_nodes, packed_tris);
     return cudaGetLastError();
 }
 

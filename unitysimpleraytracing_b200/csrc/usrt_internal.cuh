@@ -50,12 +50,12 @@ cudaError_t launch_distribute_keys(const uint32_t* src, uint32_t* dst, uint32_t 
 uint64_t distribute_status_bytes(uint32_t n);
 // K4
 cudaError_t launch_construct_tree(const uint32_t* keys, uint32_t n, usrt_internal_node* internal,
-                                  usrt_leaf_node* leaf, cudaStream_t stream);
+                                  usrt_leaf_node* leaf, uint32_t* up_internal, uint32_t* up_leaf, cudaStream_t stream);
 // K5 (+ packed traversal arrays)
 cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
                                  const usrt_triangle* tris, const usrt_internal_node* internal,
-                                 const usrt_leaf_node* leaf, usrt_aabb* bvh, uint32_t* counters, float4* packed_nodes,
-                                 float4* packed_tris, cudaStream_t stream);
+                                 const uint32_t* up_internal, const uint32_t* up_leaf, usrt_aabb* bvh, uint32_t* counters,
+                                 float4* packed_nodes, float4* packed_tris, cudaStream_t stream);
 // validator (MeshBufferContainer.cs:181-195)
 cudaError_t launch_count_corrupted(const usrt_leaf_node* leaf, const usrt_internal_node* internal, uint32_t n,
                                    uint32_t* out2, cudaStream_t stream);
