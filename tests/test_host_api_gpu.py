@@ -96,3 +96,22 @@ def test_runs_on_a_torch_stream_with_device_buffers(usrt, oracle):
     got = out.cpu().numpy().view(oracle.RAYCAST_RESULT)
     assert got.tobytes() == ref.trace_rays(rays).tobytes()
     ctx.close()
+
+
+def test_pinned_host_frame_is_written_directly_and_matches_staged_copy(usrt):
+    """usrt_trace_primary writes hit records straight into page-locked host memory (zero-copy) and into
+    pageable memory through a staged copy; both must hold the same frame, including partial row ranges."""
+    import torch
+    tris = meshes.scene_c1(); cam = meshes.SCENE_SOUP_CAMERA
+    ctx = usrt.Context(len(tris)); ctx.upload_triangles(tris); ctx.rebuild()
+    w, h = 321, 123
+    pageable = ctx.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    pinned_t = torch.zeros(w * h * 16, dtype=torch.uint8).pin_memory()
+    pinned = pinned_t.numpy().view(pageable.dtype)
+    ctx.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], out=pinned)
+    assert pinned.tobytes() == pageable.tobytes()
+    pinned[:] = 0
+    ctx.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], 40, 77, out=pinned)
+    assert pinned[40 * w:77 * w].tobytes() == pageable[40 * w:77 * w].tobytes()
+    assert not pinned[:40 * w].view(np.uint8).any() and not pinned[77 * w:].view(np.uint8).any()
+    ctx.close()

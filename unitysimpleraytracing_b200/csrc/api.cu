@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -20,6 +21,7 @@ struct usrt_context {
     int device = 0;
     uint32_t capacity = 0;
     uint32_t n = 0;                       // trianglesLength
+    uint32_t dirty_n = 0;                 // slots [0, dirty_n) may differ from their initial fill
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     float whole_min = -125.0f, whole_max = 125.0f;   // MeshBufferContainer.cs:9-15
@@ -91,17 +93,22 @@ int bind_device(usrt_context* ctx) {
 }
 
 // MeshBufferContainer.cs:108-115: keys/indices = uint.MaxValue, leaf/internal = NullLeaf (all 0xFF).
-int reset_scene_buffers(usrt_context* ctx) {
-    const size_t c = ctx->capacity;
-    CU(ctx, cudaMemsetAsync(ctx->keys, 0xFF, c * 4, ctx->stream));
-    CU(ctx, cudaMemsetAsync(ctx->keys_alt, 0xFF, c * 4, ctx->stream));
-    CU(ctx, cudaMemsetAsync(ctx->tri_index, 0xFF, c * 4, ctx->stream));
-    CU(ctx, cudaMemsetAsync(ctx->tri_index_alt, 0xFF, c * 4, ctx->stream));
-    CU(ctx, cudaMemsetAsync(ctx->leaf, 0xFF, c * sizeof(usrt_leaf_node), ctx->stream));
-    CU(ctx, cudaMemsetAsync(ctx->internal, 0xFF, c * sizeof(usrt_internal_node), ctx->stream));
-    CU(ctx, cudaMemsetAsync(ctx->tri_aabb, 0, c * sizeof(usrt_aabb), ctx->stream));
-    CU(ctx, cudaMemsetAsync(ctx->bvh, 0, c * sizeof(usrt_aabb), ctx->stream));
-    CU(ctx, cudaMemsetAsync(ctx->counters, 0, c * 4, ctx->stream));          // BVHConstructor.cs:41
+// Only slots [lo, hi) are touched: a build with n triangles rewrites every slot below n, so after a
+// full initialisation only the slots a previous, larger mesh dirtied ([n, previous n)) need restoring.
+int reset_scene_buffers(usrt_context* ctx, size_t lo, size_t hi) {
+    if (hi <= lo) return USRT_OK;
+    const size_t c = hi - lo;
+    CU(ctx, cudaMemsetAsync(ctx->keys + lo, 0xFF, c * 4, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->keys_alt + lo, 0xFF, c * 4, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->tri_index + lo, 0xFF, c * 4, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->tri_index_alt + lo, 0xFF, c * 4, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->leaf + lo, 0xFF, c * sizeof(usrt_leaf_node), ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->tri_aabb + lo, 0, c * sizeof(usrt_aabb), ctx->stream));
+    // internal nodes / node boxes are written for [0, n-1): slot n-1 of the new mesh must be restored too
+    const size_t ilo = lo > 0 ? lo - 1 : 0;
+    CU(ctx, cudaMemsetAsync(ctx->internal + ilo, 0xFF, (hi - ilo) * sizeof(usrt_internal_node), ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->bvh + ilo, 0, (hi - ilo) * sizeof(usrt_aabb), ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)ctx->capacity * 4, ctx->stream));   // BVHConstructor.cs:41
     return USRT_OK;
 }
 
@@ -208,7 +215,7 @@ int usrt_create(int device, uint32_t capacity, usrt_context** out) {
         CU(ctx, cudaMemsetAsync(ctx->triangles, 0, c * sizeof(usrt_triangle), ctx->stream));
         for (auto& ev : ctx->ev) CU(ctx, cudaEventCreate(&ev));
         for (auto& ev : ctx->sort_ev) CU(ctx, cudaEventCreate(&ev));
-        int r = reset_scene_buffers(ctx);
+        int r = reset_scene_buffers(ctx, 0, capacity);
         if (r != USRT_OK) return r;
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         return USRT_OK;
@@ -275,7 +282,8 @@ int usrt_upload_triangles(usrt_context* ctx, const usrt_triangle* host_triangles
     NEED_CTX(ctx);
     if (!host_triangles || n > ctx->capacity) return fail(ctx, USRT_ERR_ARG, "upload_triangles: n=%u capacity=%u", n, ctx->capacity);
     if (int r = bind_device(ctx)) return r;
-    if (int r = reset_scene_buffers(ctx)) return r;
+    if (int r = reset_scene_buffers(ctx, n, ctx->dirty_n)) return r;
+    ctx->dirty_n = n;
     CU(ctx, cudaMemcpyAsync(ctx->triangles, host_triangles, (size_t)n * sizeof(usrt_triangle), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n = n;
@@ -287,7 +295,8 @@ int usrt_set_triangles_device(usrt_context* ctx, const void* dev_triangles, uint
     NEED_CTX(ctx);
     if (!dev_triangles || n > ctx->capacity) return fail(ctx, USRT_ERR_ARG, "set_triangles_device: n=%u capacity=%u", n, ctx->capacity);
     if (int r = bind_device(ctx)) return r;
-    if (int r = reset_scene_buffers(ctx)) return r;
+    if (int r = reset_scene_buffers(ctx, n, ctx->dirty_n)) return r;
+    ctx->dirty_n = n;
     CU(ctx, cudaMemcpyAsync(ctx->triangles, dev_triangles, (size_t)n * sizeof(usrt_triangle), cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->n = n;
     ctx->stage = ST_TRIS;
@@ -458,14 +467,30 @@ int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plan
     p.y0 = y0; p.y1 = y1;
     p.block_rows = 1; p.shard = 0; p.num_shards = 0; p.local_rows = 0;
     TraceScene s{ctx->packed_nodes, ctx->packed_tris, ctx->bvh};
-    CU(ctx, launch_trace_primary(s, p, ctx->hits, ctx->trace_mode, ctx->stream));
-    ctx->launches += (y1 > y0) ? 1 : 0;
-    if (host_out && y1 > y0) {
-        const size_t off = (size_t)y0 * width;
-        CU(ctx, cudaMemcpyAsync(host_out + off, ctx->hits + off, (size_t)(y1 - y0) * width * sizeof(usrt_raycast_result),
-                                cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const int rows = y1 - y0;
+    if (!host_out || rows <= 0) {
+        CU(ctx, launch_trace_primary(s, p, ctx->hits, ctx->trace_mode, ctx->stream));
+        ctx->launches += rows > 0 ? 1 : 0;
+        return USRT_OK;
     }
+    // Host readback. If host_out is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) the
+    // kernel writes each hit record to it directly as well (posted PCIe writes, 128-B runs per warp
+    // row), so the 16 B/ray transfer overlaps the traversal instead of following it. Pageable
+    // memory takes a staged copy after the kernel.
+    cudaPointerAttributes attr;
+    usrt_raycast_result* alias = nullptr;
+    if (cudaPointerGetAttributes(&attr, host_out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        alias = static_cast<usrt_raycast_result*>(attr.devicePointer);
+    else
+        cudaGetLastError();                               // clear the "not a CUDA pointer" status
+    CU(ctx, launch_trace_primary(s, p, ctx->hits, ctx->trace_mode, ctx->stream, alias));
+    ctx->launches += 1;
+    if (!alias) {
+        const size_t off = (size_t)y0 * width;
+        CU(ctx, cudaMemcpyAsync(host_out + off, ctx->hits + off, (size_t)rows * width * sizeof(usrt_raycast_result),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return USRT_OK;
 }
 

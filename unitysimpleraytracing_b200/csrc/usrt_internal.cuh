@@ -76,8 +76,9 @@ struct PrimaryParams {
     // ((lr / block_rows) * num_shards + shard) * block_rows + lr % block_rows; record index lr*width + x
     int block_rows, shard, num_shards, local_rows;
 };
+// host_alias (optional): device-visible alias of a page-locked HOST frame; records are written to both.
 cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p, usrt_raycast_result* out, int mode,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, usrt_raycast_result* host_alias = nullptr);
 cudaError_t launch_trace_rays(const TraceScene& scene, const float4* rays, uint64_t num_rays, usrt_raycast_result* out,
                               int mode, cudaStream_t stream);
 
