@@ -20,12 +20,21 @@ namespace usrt {
 
 namespace {
 
-constexpr int kBlock = 512;                 // threads per tile CTA (16 warps)
-constexpr int kIPT = 16;                    // pairs per thread
-constexpr int kTile = kBlock * kIPT;        // 8192 pairs per tile
-constexpr int kWarps = kBlock / 32;
-constexpr int kCtasPerSM = 2;
-static_assert(kBlock >= kRadix, "one thread per digit in the scan / look-back step");
+// Tile shapes. Large sorts are bound by per-key shared-memory work, so tiles are big (fewer look-back
+// steps, longer coalesced runs per digit); small sorts (the 1M-triangle rebuild) are latency-bound,
+// so tiles are small and many CTAs run at once.
+template <int BLOCK, int IPT, int CTAS> struct TileCfg {
+    static constexpr int kBlock = BLOCK;            // threads per tile CTA
+    static constexpr int kIPT = IPT;                // pairs per thread
+    static constexpr int kTile = BLOCK * IPT;       // pairs per tile
+    static constexpr int kWarps = BLOCK / 32;
+    static constexpr int kCtasPerSM = CTAS;
+    static constexpr int kMatchBytes = kWarps * kRadix * 8;
+    static_assert(BLOCK >= kRadix, "one thread per digit in the scan / look-back step");
+};
+using BigTile = TileCfg<512, 16, 2>;                // 8192 pairs
+using SmallTile = TileCfg<256, 8, 6>;               // 2048 pairs
+constexpr uint64_t kSmallSortLimit = 1ull << 18;    // below this many pairs use SmallTile (measured: 2^20 is faster with BigTile)
 constexpr uint32_t kHeaderWords = 64;       // tile counters live in the first 256 B of the status buffer
 
 // look-back status word: flag in the top bits, running count below. 32-bit words hold counts
@@ -132,23 +141,24 @@ __global__ void __launch_bounds__(kSortPasses * kRadix) k_scan_histogram(uint32_
 // rounds. The lowest peer lane then writes {0, count + popc(mask)} -- clearing the mask and
 // advancing the running count in one store. Measured on B200 this costs ~7 SM-cycles per warp-round
 // against ~25 for an 8-ballot match and ~60 for match.any (tools/micro/match_bench.cu).
-constexpr int kMatchBytes = kWarps * kRadix * 8;
-template <bool kHasValues> struct PassSmem {
-    static constexpr int kPairBytes = kTile * (kHasValues ? 8 : 4);
-    static constexpr int kTotal = kMatchBytes + kPairBytes + kRadix * 4 + kWarps * 4 + 16;
+template <typename Cfg, bool kHasValues> struct PassSmem {
+    static constexpr int kPairBytes = Cfg::kTile * (kHasValues ? 8 : 4);
+    static constexpr int kTotal = Cfg::kMatchBytes + kPairBytes + kRadix * 4 + Cfg::kWarps * 4 + 16;
 };
 
-template <typename StatusT, bool kHasValues>
-__global__ void __launch_bounds__(kBlock, kCtasPerSM)
+template <typename Cfg, typename StatusT, bool kHasValues>
+__global__ void __launch_bounds__(Cfg::kBlock, Cfg::kCtasPerSM)
 k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ digit_base /* [256] */,
            uint32_t* __restrict__ tile_counter, StatusT* __restrict__ status /* [tiles][256], zeroed */) {
     using ST = StatusTraits<StatusT>;
+    constexpr int kBlock = Cfg::kBlock, kIPT = Cfg::kIPT, kTile = Cfg::kTile, kWarps = Cfg::kWarps;
+    constexpr int kMatchBytes = Cfg::kMatchBytes;
     extern __shared__ __align__(16) unsigned char smem[];
     uint2* s_match = reinterpret_cast<uint2*>(smem);                              // [kWarps][256]
     uint2* s_pairs = reinterpret_cast<uint2*>(smem + kMatchBytes);                // kHasValues
     uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem + kMatchBytes);           // !kHasValues
-    uint32_t* s_global_off = reinterpret_cast<uint32_t*>(smem + kMatchBytes + PassSmem<kHasValues>::kPairBytes);
+    uint32_t* s_global_off = reinterpret_cast<uint32_t*>(smem + kMatchBytes + PassSmem<Cfg, kHasValues>::kPairBytes);
     uint32_t* s_scan = s_global_off + kRadix;
     uint32_t* s_tile_id = s_scan + kWarps;
 
@@ -315,24 +325,30 @@ inline uint32_t histogram_grid(uint64_t count) {
     const uint64_t vec_work = (count + 4 * kHistThreads - 1) / (4 * kHistThreads);
     return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(vec_work, 1), (uint64_t)kNumSMs);
 }
-inline uint32_t num_tiles(uint64_t count) { return (uint32_t)((count + kTile - 1) / kTile); }
+inline uint32_t tile_pairs(uint64_t count) { return count < kSmallSortLimit ? SmallTile::kTile : BigTile::kTile; }
+inline uint32_t num_tiles(uint64_t count) { return (uint32_t)((count + tile_pairs(count) - 1) / tile_pairs(count)); }
 inline bool wide_status(uint64_t count) { return count >= (1ull << 30); }
 inline uint64_t status_words_bytes(uint64_t count) { return (uint64_t)num_tiles(count) * kRadix * (wide_status(count) ? 8 : 4); }
+
+template <typename Cfg, typename StatusT, bool kHasValues>
+cudaError_t launch_pass(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint64_t count, int shift,
+                        const uint32_t* digit_base, uint32_t* tile_counter, void* status, cudaStream_t stream) {
+    constexpr int smem = PassSmem<Cfg, kHasValues>::kTotal;
+    cudaFuncSetAttribute(k_onesweep<Cfg, StatusT, kHasValues>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_onesweep<Cfg, StatusT, kHasValues><<<num_tiles(count), Cfg::kBlock, smem, stream>>>(
+        ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter, static_cast<StatusT*>(status));
+    return cudaGetLastError();
+}
 
 template <typename StatusT>
 cudaError_t run_pass(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint64_t count, int shift,
                      const uint32_t* digit_base, uint32_t* tile_counter, void* status, cudaStream_t stream) {
-    const uint32_t tiles = num_tiles(count);
-    if (vi != nullptr) {
-        cudaFuncSetAttribute(k_onesweep<StatusT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PassSmem<true>::kTotal);
-        k_onesweep<StatusT, true><<<tiles, kBlock, PassSmem<true>::kTotal, stream>>>(
-            ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter, static_cast<StatusT*>(status));
-    } else {
-        cudaFuncSetAttribute(k_onesweep<StatusT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PassSmem<false>::kTotal);
-        k_onesweep<StatusT, false><<<tiles, kBlock, PassSmem<false>::kTotal, stream>>>(
-            ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter, static_cast<StatusT*>(status));
-    }
-    return cudaGetLastError();
+    const bool small = count < kSmallSortLimit;
+    if (vi != nullptr)
+        return small ? launch_pass<SmallTile, StatusT, true>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream)
+                     : launch_pass<BigTile, StatusT, true>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
+    return small ? launch_pass<SmallTile, StatusT, false>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream)
+                 : launch_pass<BigTile, StatusT, false>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
 }
 
 }  // namespace
