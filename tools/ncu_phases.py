@@ -16,7 +16,7 @@ for i, r in enumerate(data):
     sm = int(r[idx['# Samples']] or 0)
     acc += sm
     execs += int(r[idx['Instructions Executed']] or 0)
-    wf += int(float(r[idx['L1 Wavefronts Shared']] or 0)); wfx += int(float(r[idx['L1 Wavefronts Shared Excessive']] or 0))
+    wf += int(float(r[idx.get("L1 Wavefronts Shared", 0)] or 0)) if "L1 Wavefronts Shared" in idx else 0; wfx += int(float(r[idx["L1 Wavefronts Shared Excessive"]] or 0)) if "L1 Wavefronts Shared Excessive" in idx else 0
     for h in stalls:
         accs[h] = accs.get(h, 0) + int(r[idx[h]] or 0)
     if 'BAR.SYNC' in r[idx['Source']] or 'EXIT' in r[idx['Source']]:

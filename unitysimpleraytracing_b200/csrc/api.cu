@@ -35,8 +35,9 @@ struct usrt_context {
     usrt_aabb* bvh = nullptr;
     usrt_leaf_node* leaf = nullptr;
     usrt_internal_node* internal = nullptr;
-    // BVHConstructor.cs:16 _atomics
-    uint32_t* counters = nullptr;
+    // stands in for BVHConstructor.cs:16 _atomics: per-node exchange slots (2 x 16 B), empty = 0xFF..,
+    // emptied again by the merging arrival, so ConstructBVH is re-runnable without a memset
+    float4* slots = nullptr;
     uint32_t *up_internal = nullptr, *up_leaf = nullptr;   // K4 -> K5 parent links (side + locality bits)
     // traversal-side arrays written by K5
     float4* packed_nodes = nullptr;
@@ -108,7 +109,7 @@ int reset_scene_buffers(usrt_context* ctx, size_t lo, size_t hi) {
     const size_t ilo = lo > 0 ? lo - 1 : 0;
     CU(ctx, cudaMemsetAsync(ctx->internal + ilo, 0xFF, (hi - ilo) * sizeof(usrt_internal_node), ctx->stream));
     CU(ctx, cudaMemsetAsync(ctx->bvh + ilo, 0, (hi - ilo) * sizeof(usrt_aabb), ctx->stream));
-    CU(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)ctx->capacity * 4, ctx->stream));   // BVHConstructor.cs:41
+    CU(ctx, cudaMemsetAsync(ctx->slots, 0xFF, (size_t)ctx->capacity * 2 * sizeof(float4), ctx->stream));   // BVHConstructor.cs:41
     return USRT_OK;
 }
 
@@ -167,7 +168,7 @@ int do_tree(usrt_context* ctx) {
 
 int do_bvh(usrt_context* ctx) {
     CU(ctx, launch_construct_bvh(ctx->n, ctx->tri_index, ctx->tri_aabb, ctx->triangles, ctx->internal, ctx->up_internal,
-                                 ctx->up_leaf, ctx->bvh, ctx->counters, ctx->packed_nodes, ctx->packed_tris, ctx->stream));
+                                 ctx->up_leaf, ctx->bvh, ctx->slots, ctx->packed_nodes, ctx->packed_tris, ctx->stream));
     ctx->launches += 1;
     ctx->stage |= ST_BVH;
     return USRT_OK;
@@ -204,7 +205,7 @@ int usrt_create(int device, uint32_t capacity, usrt_context** out) {
         CU(ctx, cudaMalloc(&ctx->bvh, c * sizeof(usrt_aabb)));
         CU(ctx, cudaMalloc(&ctx->leaf, c * sizeof(usrt_leaf_node)));
         CU(ctx, cudaMalloc(&ctx->internal, c * sizeof(usrt_internal_node)));
-        CU(ctx, cudaMalloc(&ctx->counters, c * 4));
+        CU(ctx, cudaMalloc(&ctx->slots, c * 2 * sizeof(float4)));
         CU(ctx, cudaMalloc(&ctx->up_internal, c * 4));
         CU(ctx, cudaMalloc(&ctx->up_leaf, c * 4));
         CU(ctx, cudaMalloc(&ctx->packed_nodes, c * 4 * sizeof(float4)));
@@ -235,7 +236,7 @@ int usrt_destroy(usrt_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     void* ptrs[] = {ctx->keys, ctx->keys_alt, ctx->tri_index, ctx->tri_index_alt, ctx->triangles, ctx->tri_aabb,
-                    ctx->bvh, ctx->leaf, ctx->internal, ctx->counters, ctx->up_internal, ctx->up_leaf, ctx->packed_nodes, ctx->packed_tris,
+                    ctx->bvh, ctx->leaf, ctx->internal, ctx->slots, ctx->up_internal, ctx->up_leaf, ctx->packed_nodes, ctx->packed_tris,
                     ctx->scan_status, ctx->small, ctx->hits, ctx->rays};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -142,7 +142,7 @@ struct KeyView {
 // Besides the reference's node arrays, K4 emits one private 32-bit "up link" per node for K5:
 //   bits 0..29 parent index | bit 30 = this node is its parent's RIGHT child | bit 31 = the parent's
 //   whole leaf range lies inside one kRefitBlock-aligned block of leaves (K5 merges it in shared memory).
-constexpr int kRefitBlock = 512;                 // leaves per K5 CTA
+constexpr int kRefitBlock = 128;                 // leaves per K5 CTA
 constexpr uint32_t kUpRight = 1u << 30, kUpLocal = 1u << 31, kUpParentMask = (1u << 30) - 1;
 
 __global__ void __launch_bounds__(256) k_construct_tree(const uint32_t* __restrict__ codes, uint32_t n,
@@ -215,19 +215,30 @@ __global__ void __launch_bounds__(256) k_construct_tree(const uint32_t* __restri
 __device__ __forceinline__ float sel_min(float a, float b) { return a < b ? a : b; }
 __device__ __forceinline__ float sel_max(float a, float b) { return a > b ? a : b; }
 
+__device__ __forceinline__ float4 atom_exch_128(float4* p, float4 v) {
+    const uint64_t lo = (uint64_t)__float_as_uint(v.x) | ((uint64_t)__float_as_uint(v.y) << 32);
+    const uint64_t hi = (uint64_t)__float_as_uint(v.z) | ((uint64_t)__float_as_uint(v.w) << 32);
+    uint64_t olo, ohi;
+    asm volatile("{\n\t.reg .b128 vin, vout;\n\tmov.b128 vin, {%2, %3};\n\t"
+                 "atom.relaxed.gpu.global.exch.b128 vout, [%4], vin;\n\tmov.b128 {%0, %1}, vout;\n\t}"
+                 : "=l"(olo), "=l"(ohi) : "l"(lo), "l"(hi), "l"(p) : "memory");
+    return make_float4(__uint_as_float((uint32_t)olo), __uint_as_float((uint32_t)(olo >> 32)),
+                       __uint_as_float((uint32_t)ohi), __uint_as_float((uint32_t)(ohi >> 32)));
+}
+
 // One CTA owns kRefitBlock consecutive leaves. A node whose leaf range lies inside the block is
 // "local": its two arrivals meet in shared memory -- each child deposits {box, ref} in its own slot,
 // bumps a shared-memory counter, and the second arrival merges -- so ~99 % of the n-1 merges need
 // no global atomic, no gpu-scope fence and no global re-read of the sibling box. Nodes spanning
-// blocks use the reference's global protocol (BVH.compute:184-215): counter RMW, first arrival
-// leaves, second loads the sibling box and merges.
+// blocks keep the reference's rule (BVH.compute:184-215: first arrival leaves, second merges) but swap
+// their boxes through 128-bit atomic exchanges instead of a counter + fence + reload.
 __global__ void __launch_bounds__(kRefitBlock) k_construct_bvh(uint32_t n, const uint32_t* __restrict__ sorted_indices,
                                                                const float4* __restrict__ tri_aabb,
                                                                const float4* __restrict__ tris,
                                                                const usrt_internal_node* __restrict__ internal,
                                                                const uint32_t* __restrict__ up_internal,
                                                                const uint32_t* __restrict__ up_leaf,
-                                                               float4* bvh, uint32_t* counters, float4* packed_nodes,
+                                                               float4* bvh, float4* slots, float4* packed_nodes,
                                                                float4* __restrict__ packed_tris) {
     __shared__ float4 s_slot[kRefitBlock][2][2];                       // [local node][side]{min|ref, max}
     __shared__ uint32_t s_count[kRefitBlock];
@@ -272,32 +283,27 @@ __global__ void __launch_bounds__(kRefitBlock) k_construct_bvh(uint32_t n, const
             smax = s_slot[lp][side ^ 1u][1];
             sib_ref = __float_as_uint(smin.w);
         } else {
-            // Everything that does not depend on the counter is requested first, so that per level the
-            // serial chain is only: store ack -> counter RMW -> sibling box. (The top ~30 levels of the
-            // tree span blocks and are walked one after the other; their latency is the kernel's.)
+            // Cross-block node: the two arrivals swap boxes through a 32-byte slot with two 128-bit
+            // atomic exchanges (ATOMG.EXCH.128). The box travels INSIDE the atomic, so there is no
+            // store -> fence -> counter -> sibling-load chain per level, and the ~30 levels that span
+            // blocks cost one L2 round trip each. Word 0 = {min.xyz, child ref}, word 1 = {max.xyz,
+            // side}; .w == 0xFFFFFFFF marks an empty word. Whoever finds word 0 empty arrived first and
+            // leaves (BVH.compute:184-189); the other one merges. It may have overtaken the first
+            // arrival on word 1: then it re-exchanges its own max until the sibling's shows up (the first
+            // arrival's second exchange is unconditional, so the wait is bounded). The merger finally
+            // empties the slot again, which keeps the protocol re-runnable without a memset.
             next_link = __ldg(up_internal + parent);
-            const uint32_t* node = reinterpret_cast<const uint32_t*>(internal + parent);
-            const uint2 sib = __ldg(reinterpret_cast<const uint2*>(node + (side ? 0 : 2)));   // the other child
-            if (sib.y != USRT_INTERNAL_NODE) {                         // leaf sibling: read-only inputs
-                const uint32_t stri = __ldg(sorted_indices + sib.x);
-                smin = __ldg(tri_aabb + (size_t)stri * 2);
-                smax = __ldg(tri_aabb + (size_t)stri * 2 + 1);
-                sib_ref = 0x80000000u | sib.x;
-            }
-            // XOR instead of CAS(0->1): same first/second decision and the counter is back to 0
-            // afterwards (re-runnable; the reference zeroes it once, BVHConstructor.cs:41). Release at
-            // gpu scope publishes our box store of the previous level before the counter flips. The
-            // acquire side is the control dependency on `old` plus ld.global.cg below: the sibling box
-            // is read from L2 (the coherence point) after the RMW returned, so no L1 line can be stale
-            // and the L1-wide invalidate an acquire would cost (CCTL.IVALL) is not needed.
-            uint32_t old;
-            asm volatile("atom.release.gpu.global.xor.b32 %0, [%1], 1;" : "=r"(old) : "l"(counters + parent) : "memory");
-            if (old == 0) break;
-            if (sib.y == USRT_INTERNAL_NODE) {                         // :197-213; written this launch => .cg
-                smin = __ldcg(bvh + (size_t)sib.x * 2);
-                smax = __ldcg(bvh + (size_t)sib.x * 2 + 1);
-                sib_ref = sib.x;
-            }
+            float4* slot = slots + (size_t)parent * 2;
+            const float4 mine1 = make_float4(bmax.x, bmax.y, bmax.z, __uint_as_float(side));
+            smin = atom_exch_128(slot, make_float4(bmin.x, bmin.y, bmin.z, __uint_as_float(cur_ref)));
+            smax = atom_exch_128(slot + 1, mine1);
+            if (__float_as_uint(smin.w) == USRT_NULL) break;
+            while (__float_as_uint(smax.w) != (side ^ 1u)) smax = atom_exch_128(slot + 1, mine1);
+            sib_ref = __float_as_uint(smin.w);
+            const float4 empty = make_float4(__uint_as_float(USRT_NULL), __uint_as_float(USRT_NULL), __uint_as_float(USRT_NULL),
+                                             __uint_as_float(USRT_NULL));
+            __stcg(slot, empty);
+            __stcg(slot + 1, empty);
         }
         const float4 lmin = side ? smin : bmin, lmax = side ? smax : bmax;
         const float4 rmin = side ? bmin : smin, rmax = side ? bmax : smax;
@@ -356,11 +362,11 @@ cudaError_t launch_construct_tree(const uint32_t* keys, uint32_t n, usrt_interna
 
 cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
                                  const usrt_triangle* tris, const usrt_internal_node* internal,
-                                 const uint32_t* up_internal, const uint32_t* up_leaf, usrt_aabb* bvh, uint32_t* counters,
+                                 const uint32_t* up_internal, const uint32_t* up_leaf, usrt_aabb* bvh, float4* slots,
                                  float4* packed_nodes, float4* packed_tris, cudaStream_t stream) {
     k_construct_bvh<<<(n + kRefitBlock - 1) / kRefitBlock, kRefitBlock, 0, stream>>>(
         n, sorted_indices, reinterpret_cast<const float4*>(tri_aabb), reinterpret_cast<const float4*>(tris), internal,
-        up_internal, up_leaf, reinterpret_cast<float4*>(bvh), counters, packed_nodes, packed_tris);
+        up_internal, up_leaf, reinterpret_cast<float4*>(bvh), slots, packed_nodes, packed_tris);
     return cudaGetLastError();
 }
 

@@ -54,7 +54,7 @@ cudaError_t launch_construct_tree(const uint32_t* keys, uint32_t n, usrt_interna
 // K5 (+ packed traversal arrays)
 cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
                                  const usrt_triangle* tris, const usrt_internal_node* internal,
-                                 const uint32_t* up_internal, const uint32_t* up_leaf, usrt_aabb* bvh, uint32_t* counters,
+                                 const uint32_t* up_internal, const uint32_t* up_leaf, usrt_aabb* bvh, float4* slots,
                                  float4* packed_nodes, float4* packed_tris, cudaStream_t stream);
 // validator (MeshBufferContainer.cs:181-195)
 cudaError_t launch_count_corrupted(const usrt_leaf_node* leaf, const usrt_internal_node* internal, uint32_t n,
