@@ -60,7 +60,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -142,14 +142,15 @@ def run_reference(args):
     tris, cam = build_scene()
     threads = os.cpu_count() or 1
     rows = 40
-    for _ in range(max(args.warmup, 0)):
+    for _ in range(min(max(args.warmup, 0), 2)):
         cpu_step(O, tris, cam, 8, threads)
-    samples = [cpu_step(O, tris, cam, rows, threads) for _ in range(args.steps)]
+    steps = min(args.steps, 8)          # each CPU step is ~1 s: keep the whole arm within minutes
+    samples = [cpu_step(O, tris, cam, rows, threads) for _ in range(steps)]
     step_s = statistics.mean(s["step_s"] for s in samples)
     value = W * H / step_s / 1e6
     line = {
         "impl": "reference", "metric": "Mrays/s (1080p, 1M tris; step = full LBVH rebuild incl. sort + primary-ray cast)",
-        "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32",
         "data": "synthetic",
         "config": {"workload": "configs[1]: 1,048,576-tri sphere+height-field, full rebuild + 1920x1080 primary rays",
@@ -415,8 +416,8 @@ def _flush_ms(torch, flush, stream):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

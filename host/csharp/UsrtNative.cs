@@ -45,6 +45,10 @@ namespace Usrt
         [DllImport(Lib)] public static extern int usrt_trace_primary(IntPtr ctx, int width, int height, float near, float tanHalfFov,
                                                                     [In] float[] cameraToWorldRowMajor, int y0, int y1, [Out] RaycastResult[] hostOut);
         [DllImport(Lib)] public static extern int usrt_trace_rays(IntPtr ctx, [In] float[] rays, ulong numRays, [Out] RaycastResult[] hostOut);
+        [DllImport(Lib)] public static extern int usrt_upload_texture(IntPtr ctx, [In] float[] rgba, int width, int height);
+        [DllImport(Lib)] public static extern int usrt_shade(IntPtr ctx, IntPtr devOut, [Out] ushort[] hostOutRgba16f);
+        [DllImport(Lib)] public static extern int usrt_upload_bvh(IntPtr ctx, uint n, [In] uint[] keys, [In] uint[] triangleIndex, [In] Triangle[] triangles,
+                                                                 [In] AABB[] triangleAabb, [In] AABB[] bvhData, [In] LeafNode[] leafNodes, [In] InternalNode[] internalNodes);
         [DllImport(Lib)] public static extern int usrt_download(IntPtr ctx, int buffer, IntPtr hostDst, ulong count);
         [DllImport(Lib)] public static extern int usrt_count_corrupted_nodes(IntPtr ctx, out uint leaf, out uint inner);
 

@@ -153,6 +153,25 @@ int usrt_hits_device(usrt_context* ctx, void** dev_ptr, uint64_t* count);
  * NOT part of the parity contract (reported separately). */
 int usrt_set_trace_mode(usrt_context* ctx, int mode);
 
+/* ---- importing a finished BVH ------------------------------------------------------ */
+/* Install the seven scene buffers of MeshBufferContainer.cs:87-94 from HOST arrays in the reference's
+ * layouts (n triangles: n keys / indices / triangles / triangle AABBs / leaf nodes, n-1 node AABBs and
+ * internal nodes) -- a tree that was built elsewhere: a dump of this library, or the buffers the
+ * reference's own kernels produced. The traversal-side arrays are derived on the device; afterwards the
+ * context traces exactly as if it had built the tree itself. Synchronous. */
+int usrt_upload_bvh(usrt_context* ctx, uint32_t n, const uint32_t* keys, const uint32_t* triangle_index,
+                    const usrt_triangle* triangles, const usrt_aabb* triangle_aabb, const usrt_aabb* bvh_data,
+                    const usrt_leaf_node* leaf_nodes, const usrt_internal_node* internal_nodes);
+
+/* ---- shading epilogue : Raytracing.compute:178-184 ------------------------------ */
+/* _meshTexture (Raytracing.compute:13) as width x height float4 texels, row 0 at v = 0. Synchronous. */
+int usrt_upload_texture(usrt_context* ctx, const float* host_rgba, int width, int height);
+/* Shades the hit records of the last trace call (triangle uv/normal interpolation, the scalar
+ * lightDir quirk of :181, max(0.4, .), bilinear-clamp texture fetch) into RGBA16F, 4 halfs per record,
+ * alpha = hit (the reference's R16G16B16A16_SFloat render target, RaytracingMeshDrawer.cs:56).
+ * dev_out may be NULL (an internal buffer is used); host_out may be NULL. */
+int usrt_shade(usrt_context* ctx, void* dev_out, uint16_t* host_out);
+
 /* ---- DataBuffer<T>.GetData() : DataBuffer.cs:50-54 ------------------------------------------- */
 /* Copy `count` elements of a scene buffer to host memory (synchronous). */
 int usrt_download(usrt_context* ctx, int buffer /* usrt_buffer */, void* host_dst, uint64_t count);

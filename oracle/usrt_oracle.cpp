@@ -617,6 +617,77 @@ void usrt_oracle_brute_force(const AABB* triangleAABB, const Triangle* triangleD
     });
 }
 
+// ---- shading epilogue, Raytracing.compute:178-184 --------------------------------
+// fp32 -> fp16 bits, round to nearest even (the RGBA16F render target, RaytracingMeshDrawer.cs:56).
+static uint16_t float_to_half_rn(float f) {
+    uint32_t x; std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    const uint32_t absx = x & 0x7FFFFFFFu;
+    if (absx >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | ((absx > 0x7F800000u) ? 0x0200u : 0u));   // inf / nan
+    if (absx >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);                                             // overflow -> inf
+    if (absx < 0x33000001u) return (uint16_t)sign;                                                          // underflow -> 0
+    int exp = (int)(absx >> 23) - 127 + 15;
+    uint32_t mant = absx & 0x007FFFFFu;
+    if (exp <= 0) {                                   // subnormal half
+        mant |= 0x00800000u;
+        const int shift = 14 - exp;                   // 14..24
+        uint32_t half_mant = mant >> shift;
+        const uint32_t rem = mant & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (half_mant & 1u))) half_mant++;
+        return (uint16_t)(sign | half_mant);
+    }
+    uint32_t h = ((uint32_t)exp << 10) | (mant >> 13);
+    const uint32_t rem = mant & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;   // may carry into the exponent: still correct
+    return (uint16_t)(sign | h);
+}
+
+// Texture2D.SampleLevel(linearClampSampler, uv, 0) DEFINED as: texel centres at (i + 0.5) / size, clamp
+// addressing, fp32 weights, lerp(a, b, t) = a + (b - a) * t, x first then y. Texels are float4, row 0 at v = 0.
+static void sample_bilinear_clamp(const float* tex, int tw, int th, float u, float v, float out[4]) {
+    const float x = u * (float)tw - 0.5f, y = v * (float)th - 0.5f;
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float fx = x - x0f, fy = y - y0f;
+    auto clampi = [](float f, int hi) { if (!(f >= 0.0f)) return 0; if (f > (float)hi) return hi; return (int)f; };
+    const int x0 = clampi(x0f, tw - 1), x1 = clampi(x0f + 1.0f, tw - 1);
+    const int y0 = clampi(y0f, th - 1), y1 = clampi(y0f + 1.0f, th - 1);
+    const float* c00 = tex + ((size_t)y0 * tw + x0) * 4; const float* c10 = tex + ((size_t)y0 * tw + x1) * 4;
+    const float* c01 = tex + ((size_t)y1 * tw + x0) * 4; const float* c11 = tex + ((size_t)y1 * tw + x1) * 4;
+    for (int k = 0; k < 4; ++k) {
+        const float top = c00[k] + (c10[k] - c00[k]) * fx;
+        const float bot = c01[k] + (c11[k] - c01[k]) * fx;
+        out[k] = top + (bot - top) * fy;
+    }
+}
+
+extern "C" void usrt_oracle_shade(const RaycastResult* hits, uint64_t count, const Triangle* triangleData,
+                                  const float* texture_rgba, int tex_w, int tex_h, uint16_t* out_rgba16f) {
+    // :181 `const float lightDir = normalize(float3(1,1,1))` is declared SCALAR: it keeps .x only
+    const float len = sqrtf(1.0f * 1.0f + 1.0f * 1.0f + 1.0f * 1.0f);
+    const float lightDir = 1.0f / len;
+    for (uint64_t i = 0; i < count; ++i) {
+        const RaycastResult& r = hits[i];
+        const Triangle& t = triangleData[r.triangleIndex];                       // :178 (triangle 0 for a miss)
+        const float bu = r.uv[0], bv = r.uv[1];
+        const float bw = 1 - bu - bv;
+        float uv[2], normal[3];
+        for (int k = 0; k < 2; ++k) uv[k] = bw * t.a_uv[k] + bu * t.b_uv[k] + bv * t.c_uv[k];           // :179
+        for (int k = 0; k < 3; ++k) normal[k] = bw * t.a_n[k] + bu * t.b_n[k] + bv * t.c_n[k];         // :180
+        // dot(scalar, float3): the scalar is splatted
+        const float ndotl = lightDir * normal[0] + lightDir * normal[1] + lightDir * normal[2];
+        const float shade = fmaxf(0.4f, ndotl);                                  // :183
+        float texel[4];
+        sample_bilinear_clamp(texture_rgba, tex_w, tex_h, uv[0], uv[1], texel);
+        const float a = (r.distance != MAX_FLOAT) ? 1.0f : 0.0f;                 // :184
+        out_rgba16f[i * 4 + 0] = float_to_half_rn(texel[0] * shade);
+        out_rgba16f[i * 4 + 1] = float_to_half_rn(texel[1] * shade);
+        out_rgba16f[i * 4 + 2] = float_to_half_rn(texel[2] * shade);
+        out_rgba16f[i * 4 + 3] = float_to_half_rn(a);
+    }
+}
+
+extern "C" uint16_t usrt_oracle_float_to_half(float f) { return float_to_half_rn(f); }
+
 // Leaf visiting order of the reference DFS when every box test passes (left leaf, right leaf, then
 // the RIGHT internal subtree before the LEFT one -- Raytracing.compute:148-175 push order).
 void usrt_oracle_visit_order(const uint32_t* sortedTriangleIndices, const InternalNode* internalNodes,

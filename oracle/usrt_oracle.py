@@ -197,3 +197,19 @@ def primary_rays(width, height, near, tan_half_fov, cam_to_world):
     lib().usrt_oracle_primary_rays(ctypes.c_int(width), ctypes.c_int(height), ctypes.c_float(near),
                                    ctypes.c_float(tan_half_fov), _p(m), _p(rays))
     return rays
+
+
+def shade(hits, triangle_data, texture_rgba):
+    """Raytracing.compute:178-184 on host: returns (count, 4) float16 (RGBA16F)."""
+    hits = np.ascontiguousarray(hits, RAYCAST_RESULT)
+    tex = np.ascontiguousarray(texture_rgba, np.float32)
+    th, tw = tex.shape[0], tex.shape[1]
+    out = np.zeros((len(hits), 4), np.uint16)
+    lib().usrt_oracle_shade(_p(hits), ctypes.c_uint64(len(hits)), _p(np.ascontiguousarray(triangle_data, TRIANGLE)),
+                            _p(tex), ctypes.c_int(tw), ctypes.c_int(th), _p(out))
+    return out.view(np.float16)
+
+
+def float_to_half_bits(f):
+    lib().usrt_oracle_float_to_half.restype = ctypes.c_uint16
+    return int(lib().usrt_oracle_float_to_half(ctypes.c_float(f)))

@@ -233,3 +233,49 @@ def test_row_zero_is_bottom_of_view(oracle):
     assert np.allclose(rays[:, :, 0:3], [0, 0, 15.7])
     assert np.allclose(np.linalg.norm(rays[:, :, 4:7], axis=2), 1.0, atol=1e-6)
     assert (rays[:, :, 6] < 0).all()          # the scene camera looks down world -z (Scene.unity:342)
+
+
+# ---- shading epilogue --------------------------------------------------------------------
+def test_float_to_half_matches_numpy(oracle):
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([
+        (rng.standard_normal(4000) * 10.0 ** rng.integers(-9, 6, 4000)).astype(np.float32),
+        np.array([0, -0.0, 65504, 65519.99, 65520, 1e-8, 5.96e-8, 2.98e-8, 2.9802322e-8, 2.9802326e-8, np.inf, -np.inf,
+                  6.1035156e-05, 6.0975552e-05, 1.0009766, 1.0004883, 1.0014648], np.float32)])
+    with np.errstate(over="ignore"):
+        want = vals.astype(np.float16).view(np.uint16)
+    got = np.array([oracle.float_to_half_bits(float(v)) for v in vals], np.uint16)
+    assert np.array_equal(got, want)
+
+
+def test_shade_against_numpy_restatement(oracle):
+    tris = meshes.sphere(12, 24)
+    s = oracle.Scene(tris); cam = meshes.SCENE_C2_CAMERA
+    hits = s.trace_primary(40, 30, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    rng = np.random.default_rng(1)
+    tex = rng.random((16, 20, 4), dtype=np.float32)
+    got = oracle.shade(hits, tris, tex)
+    F = np.float32
+    t = tris[hits["triangleIndex"]]
+    bu, bv = hits["uv"][:, 0], hits["uv"][:, 1]
+    bw = ((F(1) - bu).astype(F) - bv).astype(F)
+    def interp(a, b, c):
+        return (((bw[:, None] * a).astype(F) + (bu[:, None] * b).astype(F)).astype(F) + (bv[:, None] * c).astype(F)).astype(F)
+    uv = interp(t["a_uv"], t["b_uv"], t["c_uv"]); nrm = interp(t["a_normal"], t["b_normal"], t["c_normal"])
+    light = F(1) / np.sqrt(F(3), dtype=F)
+    ndotl = (((light * nrm[:, 0]).astype(F) + (light * nrm[:, 1]).astype(F)).astype(F) + (light * nrm[:, 2]).astype(F)).astype(F)
+    shade = np.fmax(F(0.4), ndotl)
+    th, tw = tex.shape[:2]
+    x = ((uv[:, 0] * F(tw)).astype(F) - F(0.5)).astype(F); y = ((uv[:, 1] * F(th)).astype(F) - F(0.5)).astype(F)
+    x0f, y0f = np.floor(x), np.floor(y)
+    fx, fy = (x - x0f).astype(F), (y - y0f).astype(F)
+    x0 = np.clip(x0f, 0, tw - 1).astype(int); x1 = np.clip(x0f + 1, 0, tw - 1).astype(int)
+    y0 = np.clip(y0f, 0, th - 1).astype(int); y1 = np.clip(y0f + 1, 0, th - 1).astype(int)
+    def lerp(a, b, w):
+        return (a + ((b - a).astype(F) * w[:, None]).astype(F)).astype(F)
+    texel = lerp(lerp(tex[y0, x0], tex[y0, x1], fx), lerp(tex[y1, x0], tex[y1, x1], fx), fy)
+    rgb = (texel[:, :3] * shade[:, None]).astype(F).astype(np.float16)
+    alpha = (hits["distance"] != oracle.max_float()).astype(np.float16)
+    assert np.array_equal(got[:, :3].view(np.uint16), rgb.view(np.uint16))
+    assert np.array_equal(got[:, 3], alpha)
+    assert (alpha == 1).sum() > 100

@@ -177,3 +177,84 @@ def test_culled_mode_is_reported_separately(usrt, oracle):
     differing = int((strict["triangleIndex"] != culled["triangleIndex"]).sum())
     assert differing <= len(strict) // 1000
     d.OnDestroy()
+
+
+def test_large_soup_build_and_incoherent_rays(usrt, oracle):
+    """BASELINE config 4 shape at 2^22 triangles (the 2^24 run is recorded in profiles/): full build
+    parity by digest of every buffer, plus incoherent random rays and a small primary frame."""
+    import hashlib
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    n = 1 << 22
+    tris = meshes.uniform_soup(n, seed=0x5EED0004)
+    ref = oracle.Scene(tris)
+    ctx = usrt.Context(n)
+    ctx.upload_triangles(tris)
+    ctx.rebuild()
+    assert sha(ctx.download(_lib.BUF_KEYS)) == sha(ref.sortedMortonCodes)
+    assert sha(ctx.download(_lib.BUF_TRIANGLE_INDEX)) == sha(ref.sortedTriangleIndices)
+    assert sha(ctx.download(_lib.BUF_INTERNAL_NODES, n - 1)) == sha(ref.internalNodes[:n - 1])
+    assert sha(ctx.download(_lib.BUF_LEAF_NODES)) == sha(ref.leafNodes)
+    assert sha(ctx.download(_lib.BUF_BVH_DATA, n - 1)) == sha(ref.bvhData[:n - 1])
+    assert ctx.count_corrupted_nodes() == (0, 0)
+    rays = meshes.incoherent_rays(3000, seed=0x5EED0005)
+    assert _same(ctx.trace_rays(rays), ref.trace_rays(rays, threads=16))
+    cam = meshes.SCENE_SOUP_CAMERA
+    got = ctx.trace_primary(48, 27, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    assert _same(got, ref.trace_primary(48, 27, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], threads=16))
+    ctx.close()
+
+
+def _checker_texture(w=64, h=48, seed=3):
+    rng = np.random.default_rng(seed)
+    tex = rng.random((h, w, 4), dtype=np.float32)
+    tex[::7, :, :3] *= 40.0            # some values beyond [0,1] so fp16 rounding/overflow paths are hit
+    return tex
+
+
+@pytest.mark.parametrize("name,cam", [("sphere", "SCENE_C2_CAMERA"), ("soup4097", "SCENE_SOUP_CAMERA"), ("refgrid", "REFERENCE_CAMERA")])
+def test_shading_epilogue(usrt, oracle, name, cam):
+    """SURVEY 8(f)-1, Raytracing.compute:178-184: RGBA16F image bit-exact against the oracle, misses included
+    (alpha 0, colour of triangle 0 as the reference computes it)."""
+    tris = _mesh(name); cam = getattr(meshes, cam)
+    w, h = 160, 90
+    tex = _checker_texture()
+    d = usrt.RaytracingMeshDrawer(tris).Awake()
+    ctx = d.container.ctx
+    ctx.upload_texture(tex)
+    hits = d.Update(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    img = ctx.shade()
+    want = oracle.shade(hits, tris, tex)
+    assert img.shape == (w * h, 4)
+    assert img.view(np.uint16).tobytes() == want.view(np.uint16).tobytes()
+    hit = hits["distance"] != oracle.max_float()
+    assert np.array_equal(img[:, 3] == 1.0, hit) and np.array_equal(img[:, 3] == 0.0, ~hit)
+    d.OnDestroy()
+
+
+def test_bvh_dump_and_reload(usrt, oracle, tmp_path):
+    """save the seven buffers, load them into a FRESH context (no rebuild) and trace; also
+    install a BVH that was built elsewhere -- here by the oracle -- straight from host arrays."""
+    from unitysimpleraytracing_b200 import bvh_io
+    tris = _mesh("c1"); cam = meshes.SCENE_SOUP_CAMERA
+    n = len(tris)
+    a = usrt.Context(n); a.upload_triangles(tris); a.rebuild()
+    want = a.trace_primary(96, 54, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    path = str(tmp_path / "scene.usrtbvh")
+    saved = bvh_io.save_bvh(a, path)
+    a.close()
+    b = usrt.Context(n + 7)
+    assert bvh_io.load_bvh(b, path) == n
+    assert _same(b.trace_primary(96, 54, cam["near"], cam["tan_half_fov"], cam["cam_to_world"]), want)
+    for name, buf in zip(("keys", "triangleIndex", "triangleAABB", "bvhData", "leafNodes", "internalNodes"),
+                         (_lib.BUF_KEYS, _lib.BUF_TRIANGLE_INDEX, _lib.BUF_TRIANGLE_AABB, _lib.BUF_BVH_DATA,
+                          _lib.BUF_LEAF_NODES, _lib.BUF_INTERNAL_NODES)):
+        assert _same(b.download(buf, len(saved[name])), saved[name]), name
+    rays = meshes.incoherent_rays(2000, seed=11)
+    ref = oracle.Scene(tris)
+    c = usrt.Context(n)
+    bvh_io.upload_bvh(c, n, dict(keys=ref.sortedMortonCodes, triangleIndex=ref.sortedTriangleIndices, triangleData=tris,
+                                 triangleAABB=ref.triangleAABB, bvhData=ref.bvhData, leafNodes=ref.leafNodes,
+                                 internalNodes=ref.internalNodes))
+    assert _same(c.trace_rays(rays), ref.trace_rays(rays, threads=8))
+    assert _same(c.trace_primary(96, 54, cam["near"], cam["tan_half_fov"], cam["cam_to_world"]), want)
+    b.close(); c.close()

@@ -28,6 +28,7 @@ SIGNATURES = {
     "usrt_triangles_length": (_c.c_uint32, [_P]),
     "usrt_upload_triangles": (_c.c_int, [_P, _P, _c.c_uint32]),
     "usrt_set_triangles_device": (_c.c_int, [_P, _P, _c.c_uint32]),
+    "usrt_upload_bvh": (_c.c_int, [_P, _c.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
     "usrt_morton": (_c.c_int, [_P]),
     "usrt_sort": (_c.c_int, [_P]),
     "usrt_sort_pairs_device": (_c.c_int, [_P, _P, _P, _c.c_uint64]),
@@ -47,6 +48,8 @@ SIGNATURES = {
     "usrt_trace_rays_device": (_c.c_int, [_P, _P, _c.c_uint64, _P]),
     "usrt_hits_device": (_c.c_int, [_P, _c.POINTER(_P), _c.POINTER(_c.c_uint64)]),
     "usrt_set_trace_mode": (_c.c_int, [_P, _c.c_int]),
+    "usrt_upload_texture": (_c.c_int, [_P, _P, _c.c_int, _c.c_int]),
+    "usrt_shade": (_c.c_int, [_P, _P, _P]),
     "usrt_download": (_c.c_int, [_P, _c.c_int, _P, _c.c_uint64]),
     "usrt_device_ptr": (_c.c_int, [_P, _c.c_int, _c.POINTER(_P)]),
     "usrt_count_corrupted_nodes": (_c.c_int, [_P, _c.POINTER(_c.c_uint32), _c.POINTER(_c.c_uint32)]),

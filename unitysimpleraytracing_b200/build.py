@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OBJ_DIR = os.path.join(_HERE, "csrc", "build")
 LIB_PATH = os.path.join(_HERE, "libusrt_b200.so")
-SOURCES = ["api.cu", "morton.cu", "radix_sort.cu", "lbvh.cu", "trace.cu"]
+SOURCES = ["api.cu", "morton.cu", "radix_sort.cu", "lbvh.cu", "trace.cu", "shade.cu"]
 HEADERS = [os.path.join(CSRC, "usrt_internal.cuh"), os.path.join(_HERE, "..", "include", "usrt.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -52,6 +52,11 @@ struct usrt_context {
     float4* rays = nullptr;
     uint64_t rays_capacity = 0;
     int trace_mode = 0;
+    // shading epilogue
+    float4* texture = nullptr;
+    int tex_w = 0, tex_h = 0;
+    void* shaded = nullptr;
+    uint64_t shaded_capacity = 0;
     // timing
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -237,7 +242,7 @@ int usrt_destroy(usrt_context* ctx) {
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     void* ptrs[] = {ctx->keys, ctx->keys_alt, ctx->tri_index, ctx->tri_index_alt, ctx->triangles, ctx->tri_aabb,
                     ctx->bvh, ctx->leaf, ctx->internal, ctx->slots, ctx->up_internal, ctx->up_leaf, ctx->packed_nodes, ctx->packed_tris,
-                    ctx->scan_status, ctx->small, ctx->hits, ctx->rays};
+                    ctx->scan_status, ctx->small, ctx->hits, ctx->rays, ctx->texture, ctx->shaded};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     sort_scratch_free(ctx->sort);
@@ -301,6 +306,32 @@ int usrt_set_triangles_device(usrt_context* ctx, const void* dev_triangles, uint
     CU(ctx, cudaMemcpyAsync(ctx->triangles, dev_triangles, (size_t)n * sizeof(usrt_triangle), cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->n = n;
     ctx->stage = ST_TRIS;
+    return USRT_OK;
+}
+
+int usrt_upload_bvh(usrt_context* ctx, uint32_t n, const uint32_t* keys, const uint32_t* triangle_index,
+                    const usrt_triangle* triangles, const usrt_aabb* triangle_aabb, const usrt_aabb* bvh_data,
+                    const usrt_leaf_node* leaf_nodes, const usrt_internal_node* internal_nodes) {
+    NEED_CTX(ctx);
+    if (n < 2 || n > ctx->capacity || !keys || !triangle_index || !triangles || !triangle_aabb || !bvh_data || !leaf_nodes || !internal_nodes)
+        return fail(ctx, USRT_ERR_ARG, "upload_bvh: n=%u capacity=%u or null buffer", n, ctx->capacity);
+    if (int r = bind_device(ctx)) return r;
+    if (int r = reset_scene_buffers(ctx, n, ctx->dirty_n)) return r;
+    ctx->dirty_n = n;
+    const cudaMemcpyKind k = cudaMemcpyHostToDevice;
+    CU(ctx, cudaMemcpyAsync(ctx->keys, keys, (size_t)n * 4, k, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->tri_index, triangle_index, (size_t)n * 4, k, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->triangles, triangles, (size_t)n * sizeof(usrt_triangle), k, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->tri_aabb, triangle_aabb, (size_t)n * sizeof(usrt_aabb), k, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->bvh, bvh_data, (size_t)(n - 1) * sizeof(usrt_aabb), k, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->leaf, leaf_nodes, (size_t)n * sizeof(usrt_leaf_node), k, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->internal, internal_nodes, (size_t)(n - 1) * sizeof(usrt_internal_node), k, ctx->stream));
+    CU(ctx, launch_pack_traversal(n, ctx->tri_index, ctx->tri_aabb, ctx->triangles, ctx->internal, ctx->leaf, ctx->bvh,
+                                  ctx->packed_nodes, ctx->packed_tris, ctx->stream));
+    ctx->launches += 1;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n = n;
+    ctx->stage = ST_TRIS | ST_MORTON | ST_SORTED | ST_DISTRIBUTED | ST_TREE | ST_BVH;
     return USRT_OK;
 }
 
@@ -561,6 +592,45 @@ int usrt_trace_rays(usrt_context* ctx, const float* host_rays, uint64_t num_rays
         CU(ctx, cudaMemcpyAsync(host_out, ctx->hits, num_rays * sizeof(usrt_raycast_result), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return USRT_OK;
+}
+
+int usrt_upload_texture(usrt_context* ctx, const float* host_rgba, int width, int height) {
+    NEED_CTX(ctx);
+    if (!host_rgba || width <= 0 || height <= 0) return fail(ctx, USRT_ERR_ARG, "upload_texture: bad texture %dx%d", width, height);
+    if (int r = bind_device(ctx)) return r;
+    if (ctx->texture) CU(ctx, cudaFree(ctx->texture));
+    ctx->texture = nullptr;
+    const size_t bytes = (size_t)width * height * sizeof(float4);
+    CU(ctx, cudaMalloc(&ctx->texture, bytes));
+    CU(ctx, cudaMemcpyAsync(ctx->texture, host_rgba, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->tex_w = width; ctx->tex_h = height;
+    return USRT_OK;
+}
+
+int usrt_shade(usrt_context* ctx, void* dev_out, uint16_t* host_out) {
+    NEED_CTX(ctx);
+    if (!ctx->texture) return fail(ctx, USRT_ERR_STATE, "shade: no texture uploaded");
+    if (!ctx->hits || ctx->hits_count == 0) return fail(ctx, USRT_ERR_STATE, "shade: no hit records (trace first)");
+    if (int r = bind_device(ctx)) return r;
+    const uint64_t count = ctx->hits_count;
+    void* out = dev_out;
+    if (!out) {
+        if (count > ctx->shaded_capacity) {
+            if (ctx->shaded) CU(ctx, cudaFree(ctx->shaded));
+            ctx->shaded = nullptr; ctx->shaded_capacity = 0;
+            CU(ctx, cudaMalloc(&ctx->shaded, count * 8));
+            ctx->shaded_capacity = count;
+        }
+        out = ctx->shaded;
+    }
+    CU(ctx, launch_shade(ctx->hits, count, ctx->triangles, ctx->texture, ctx->tex_w, ctx->tex_h, out, ctx->stream));
+    ctx->launches += 1;
+    if (host_out) {
+        CU(ctx, cudaMemcpyAsync(host_out, out, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return USRT_OK;
 }
 

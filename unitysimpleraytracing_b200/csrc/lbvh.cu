@@ -335,7 +335,57 @@ __global__ void k_count_corrupted(const usrt_leaf_node* __restrict__ leaf, const
     if (i + 1 < n && internal[i].index == USRT_NULL && internal[i].parent == USRT_NULL) atomicAdd(out2 + 1, 1u);
 }
 
+// rebuild the traversal-side packed arrays from the seven reference-layout buffers (a BVH
+// that was built elsewhere -- loaded from a dump, or produced by the reference's own kernels).
+__global__ void __launch_bounds__(256) k_pack_traversal(uint32_t n, const uint32_t* __restrict__ sorted_indices,
+                                                        const float4* __restrict__ tri_aabb, const float4* __restrict__ tris,
+                                                        const usrt_internal_node* __restrict__ internal,
+                                                        const usrt_leaf_node* __restrict__ leaf, const float4* __restrict__ bvh,
+                                                        float4* __restrict__ packed_nodes, float4* __restrict__ packed_tris) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {                                                       // leaf slot i -> triangle copy in leaf order
+        const uint32_t tri = __ldg(sorted_indices + i);
+        const float4* t = tris + (size_t)tri * 8;
+        float4 a = __ldg(t + 0), b = __ldg(t + 1), c = __ldg(t + 2);
+        a.w = __uint_as_float(tri); b.w = 0.0f; c.w = 0.0f;
+        packed_tris[(size_t)i * 3 + 0] = a; packed_tris[(size_t)i * 3 + 1] = b; packed_tris[(size_t)i * 3 + 2] = c;
+    }
+    if (i + 1 < n) {                                                   // internal node i
+        const uint32_t* node = reinterpret_cast<const uint32_t*>(internal + i);
+        const uint2 l = __ldg(reinterpret_cast<const uint2*>(node + 0)), r = __ldg(reinterpret_cast<const uint2*>(node + 2));
+        float4 cmin[2], cmax[2];
+        uint32_t ref[2];
+        const uint2 ch[2] = {l, r};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (ch[k].y == USRT_INTERNAL_NODE) {
+                cmin[k] = __ldg(bvh + (size_t)ch[k].x * 2); cmax[k] = __ldg(bvh + (size_t)ch[k].x * 2 + 1);
+                ref[k] = ch[k].x;
+            } else {                                                   // Raytracing.compute:158: leafNodes[c].index -> sorted slot
+                const uint32_t slot = __ldg(&leaf[ch[k].x].index);
+                const uint32_t tri = __ldg(sorted_indices + slot);
+                cmin[k] = __ldg(tri_aabb + (size_t)tri * 2); cmax[k] = __ldg(tri_aabb + (size_t)tri * 2 + 1);
+                ref[k] = 0x80000000u | slot;
+            }
+        }
+        float4* pn = packed_nodes + (size_t)i * 4;
+        pn[0] = make_float4(cmin[0].x, cmin[0].y, cmin[0].z, cmax[0].x);
+        pn[1] = make_float4(cmax[0].y, cmax[0].z, cmin[1].x, cmin[1].y);
+        pn[2] = make_float4(cmin[1].z, cmax[1].x, cmax[1].y, cmax[1].z);
+        pn[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), 0.0f, 0.0f);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_pack_traversal(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
+                                  const usrt_triangle* tris, const usrt_internal_node* internal, const usrt_leaf_node* leaf,
+                                  const usrt_aabb* bvh, float4* packed_nodes, float4* packed_tris, cudaStream_t stream) {
+    k_pack_traversal<<<(n + 255) / 256, 256, 0, stream>>>(n, sorted_indices, reinterpret_cast<const float4*>(tri_aabb),
+                                                          reinterpret_cast<const float4*>(tris), internal, leaf,
+                                                          reinterpret_cast<const float4*>(bvh), packed_nodes, packed_tris);
+    return cudaGetLastError();
+}
 
 uint64_t distribute_status_bytes(uint32_t n) {
     const uint64_t tiles = ((uint64_t)n + kScanTile - 1) / kScanTile;

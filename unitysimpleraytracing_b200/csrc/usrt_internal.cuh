@@ -56,6 +56,10 @@ cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, con
                                  const usrt_triangle* tris, const usrt_internal_node* internal,
                                  const uint32_t* up_internal, const uint32_t* up_leaf, usrt_aabb* bvh, float4* slots,
                                  float4* packed_nodes, float4* packed_tris, cudaStream_t stream);
+// packed traversal arrays from the reference-layout buffers (imported BVH)
+cudaError_t launch_pack_traversal(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
+                                  const usrt_triangle* tris, const usrt_internal_node* internal, const usrt_leaf_node* leaf,
+                                  const usrt_aabb* bvh, float4* packed_nodes, float4* packed_tris, cudaStream_t stream);
 // validator (MeshBufferContainer.cs:181-195)
 cudaError_t launch_count_corrupted(const usrt_leaf_node* leaf, const usrt_internal_node* internal, uint32_t n,
                                    uint32_t* out2, cudaStream_t stream);
@@ -81,6 +85,10 @@ cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p
                                  cudaStream_t stream, usrt_raycast_result* host_alias = nullptr);
 cudaError_t launch_trace_rays(const TraceScene& scene, const float4* rays, uint64_t num_rays, usrt_raycast_result* out,
                               int mode, cudaStream_t stream);
+
+// shading epilogue
+cudaError_t launch_shade(const usrt_raycast_result* hits, uint64_t count, const usrt_triangle* tris, const float4* tex,
+                         int tw, int th, void* out_rgba16f, cudaStream_t stream);
 
 // ---- small device helpers -------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -174,6 +174,19 @@ class Context:
                                                          ctypes.c_void_p(dev_out) if dev_out else None, _ptr(out)))
         return out
 
+    def upload_texture(self, texture_rgba):
+        """(H, W, 4) float32 texels, row 0 at v = 0 (the reference's _meshTexture)."""
+        tex = np.ascontiguousarray(texture_rgba, np.float32)
+        assert tex.ndim == 3 and tex.shape[2] == 4
+        self._check(self._lib.usrt_upload_texture(self._h, _ptr(tex), tex.shape[1], tex.shape[0]))
+
+    def shade(self, count=None):
+        """Raytracing.compute:178-184 over the last trace's hit records -> (count, 4) float16 (RGBA16F)."""
+        _, n = self.hits_device()
+        out = np.zeros((n, 4), np.float16)
+        self._check(self._lib.usrt_shade(self._h, None, _ptr(out)))
+        return out
+
     def trace_rays(self, rays, out=None):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         if out is None:
