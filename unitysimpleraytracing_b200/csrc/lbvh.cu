@@ -92,23 +92,32 @@ __global__ void __launch_bounds__(kScanBlock) k_distribute_keys(const uint32_t* 
         tile_total += t;
     }
 
-    // decoupled look-back on one 64-bit word per tile: flag << 32 | running sum
-    if (tid == 0) {
+    // decoupled look-back on one 64-bit word per tile (flag << 32 | running sum), 32 predecessors per
+    // step: all tiles of a 1M-key scan start together, so a one-tile-at-a-time walk would be ~100 steps
+    if (warp == 0) {
         uint64_t* my = status + 1 + tile;
-        st_relaxed_u64(my, (tile == 0 ? kScanPrefix : kScanAggregate) | tile_total);
+        if (lane == 0) st_relaxed_u64(my, (tile == 0 ? kScanPrefix : kScanAggregate) | tile_total);
         uint32_t exclusive = 0;
-        if (tile > 0) {
-            const uint64_t* look = my - 1;
-            while (true) {
-                uint64_t s;
-                do { s = ld_relaxed_u64(look); } while ((s & kScanFlagMask) == 0);
-                exclusive += (uint32_t)s;
-                if (s & kScanPrefix) break;
-                --look;
+        int32_t base = (int32_t)tile - 1;                       // nearest predecessor of this window
+        while (base >= 0) {
+            const int32_t t = base - (int32_t)lane;
+            uint64_t s = kScanPrefix;                           // tiles before the first count as prefix 0
+            if (t >= 0) {
+                do { s = ld_relaxed_u64(status + 1 + t); } while ((s & kScanFlagMask) == 0);
             }
-            st_relaxed_u64(my, kScanPrefix | (uint32_t)(exclusive + tile_total));
+            const uint32_t has_prefix = __ballot_sync(0xFFFFFFFFu, (s & kScanPrefix) != 0);
+            const int first = __ffs(has_prefix) - 1;            // nearest lane holding an inclusive prefix (-1: none)
+            uint32_t v = (first < 0 || (int)lane <= first) ? (uint32_t)s : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            exclusive += v;
+            if (first >= 0) break;
+            base -= 32;
         }
-        s_tile_prefix = exclusive;
+        if (lane == 0) {
+            if (tile > 0) st_relaxed_u64(my, kScanPrefix | (uint32_t)(exclusive + tile_total));
+            s_tile_prefix = exclusive;
+        }
     }
     __syncthreads();
     const uint32_t add = s_tile_prefix + warp_excl;
