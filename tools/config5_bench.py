@@ -1,0 +1,57 @@
+"""torchrun tool: BASELINE config 5 shape -- a large soup (default 2^26 triangles, generated ON the GPU so no
+64 GB of host memory is needed) with the BVH replicated per rank (each rank rebuilds it: deterministic), and
+`rays_total` random incoherent rays sharded evenly across ranks; hit records all-gathered in chunks.
+Prints aggregate Mrays/s (max time over ranks).
+
+    python -m torch.distributed.run --nproc-per-node N tools/config5_bench.py --log2tris 26 --rays 33177600
+"""
+import argparse, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from unitysimpleraytracing_b200 import host
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--log2tris", type=int, default=26); ap.add_argument("--rays", type=int, default=3840 * 2160 * 4)
+ap.add_argument("--mode", type=int, default=0)
+a = ap.parse_args()
+rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
+if world > 1: dist.init_process_group("nccl", device_id=dev)
+n = 1 << a.log2tris
+g = torch.Generator(device=dev); g.manual_seed(0x5EED0006)            # same scene on every rank
+edge = 200.0 / n ** (1.0 / 3.0) * 0.75
+centre = (torch.rand((n, 1, 3), device=dev, generator=g) * 2 - 1) * 100.0
+verts = centre + (torch.rand((n, 3, 3), device=dev, generator=g) * 2 - 1) * edge
+tri = torch.zeros((n, 32), dtype=torch.float32, device=dev)            # 128-byte Triangle: a,b,c in float4 slots 0..2
+tri[:, 0:3] = verts[:, 0]; tri[:, 4:7] = verts[:, 1]; tri[:, 8:11] = verts[:, 2]
+del centre, verts
+ctx = host.Context(n, device=lr); ctx.use_torch_stream()
+ctx.set_triangles_device(tri.data_ptr(), n); ctx.enable_stage_timing(True)
+ctx.rebuild(); ctx.rebuild(); st = ctx.last_rebuild_ms()
+leaf_bad, int_bad = ctx.count_corrupted_nodes()
+per = a.rays // world
+g2 = torch.Generator(device=dev); g2.manual_seed(77 + rank)
+rays = torch.zeros((per, 8), dtype=torch.float32, device=dev)
+rays[:, 0:3] = (torch.rand((per, 3), device=dev, generator=g2) * 2 - 1) * 100.0
+d = torch.randn((per, 3), device=dev, generator=g2); rays[:, 4:7] = d / d.norm(dim=1, keepdim=True)
+out = torch.empty(per * 4, dtype=torch.float32, device=dev)
+ctx.set_trace_mode(a.mode)
+ctx.trace_rays_device(rays.data_ptr(), min(per, 1 << 16), out.data_ptr()); torch.cuda.synchronize()
+if world > 1: dist.barrier()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+ctx.trace_rays_device(rays.data_ptr(), per, out.data_ptr())
+torch.cuda.synchronize(); t_trace = time.perf_counter() - t0
+gathered = None
+if world > 1:
+    gathered = torch.empty(world * out.numel(), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(gathered, out)
+torch.cuda.synchronize(); t_all = time.perf_counter() - t0
+t = torch.tensor([t_trace, t_all], dtype=torch.float64, device=dev)
+if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+hits = int((out.view(-1, 4)[:, 0] != 2139095040.0).sum().item())
+if rank == 0:
+    print("config5: %d tris, build %.2f ms (%s), corrupted=%s | %d rays over %d GPU(s): trace %.1f ms, +gather %.1f ms -> %.1f Mrays/s aggregate (mode %d), hit fraction rank0 %.3f"
+          % (n, st["total"], ", ".join("%s %.2f" % (k, v) for k, v in st.items() if k != "total"), (leaf_bad, int_bad), per * world, world,
+             float(t[0]) * 1e3, float(t[1]) * 1e3, per * world / float(t[1]) / 1e6, a.mode, hits / per), flush=True)
+ctx.close()
+if world > 1: dist.destroy_process_group()
