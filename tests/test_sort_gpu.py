@@ -85,3 +85,41 @@ def test_partition_pass_is_stable_split_by_top_byte(usrt):
     assert np.array_equal(ov.cpu().numpy().view(np.uint32), values[order])
     assert np.array_equal(hist.cpu().numpy(), np.bincount(keys >> 24, minlength=256))
     ctx.close()
+
+
+def test_sort_with_unaligned_device_pointers(usrt):
+    """Caller buffers need not be 16-byte aligned (the histogram has a scalar head/tail around its 128-bit body)."""
+    import torch
+    dev = torch.device("cuda:0")
+    ctx = usrt.Context(2)
+    for off in (1, 2, 3):
+        n = 100003
+        keys = _keys("uniform", n, seed=off)
+        tk = torch.zeros(n + 8, dtype=torch.int32, device=dev); tv = torch.zeros(n + 8, dtype=torch.int32, device=dev)
+        tk[off:off + n] = torch.from_numpy(keys.view(np.int32)).to(dev)
+        tv[off:off + n] = torch.arange(n, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        ctx.sort_pairs_device(tk.data_ptr() + 4 * off, tv.data_ptr() + 4 * off, n)
+        ctx.sync()
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(tk[off:off + n].cpu().numpy().view(np.uint32), keys[order])
+        assert np.array_equal(tv[off:off + n].cpu().numpy().view(np.uint32), order.astype(np.uint32))
+        assert int(tk[:off].abs().sum()) == 0 and int(tk[off + n:].abs().sum()) == 0      # nothing outside the range touched
+    ctx.close()
+
+
+def test_wide_look_back_words_path():
+    """Sorts of >= 2^30 pairs use 64-bit look-back words; exercise that kernel variant at a small size through
+    the USRT_FORCE_WIDE_STATUS test hook (fresh process: the hook is read once)."""
+    import subprocess, sys, os
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, %r)\n"
+        "from unitysimpleraytracing_b200 import host\n"
+        "rng = np.random.default_rng(3); n = 300001\n"
+        "k = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32); k[::3] = k[0]; v = np.arange(n, dtype=np.uint32)\n"
+        "o = np.argsort(k, kind='stable'); kk, vv = k.copy(), v.copy()\n"
+        "c = host.Context(2); c.sort_pairs_host(kk, vv); c.close()\n"
+        "assert np.array_equal(kk, k[o]) and np.array_equal(vv, v[o]); print('wide ok')\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, USRT_FORCE_WIDE_STATUS="1"), capture_output=True, text=True)
+    assert out.returncode == 0 and "wide ok" in out.stdout, out.stderr[-2000:]

@@ -14,6 +14,9 @@
 // of the three Scan.compute dispatches), and pairs are staged in shared memory in digit order so
 // the scatter writes coalesced runs. 16 B/pair/pass => 68 algorithmic bytes per pair.
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "usrt_internal.cuh"
 
 namespace usrt {
@@ -327,7 +330,10 @@ inline uint32_t histogram_grid(uint64_t count) {
 }
 inline uint32_t tile_pairs(uint64_t count) { return count < kSmallSortLimit ? SmallTile::kTile : BigTile::kTile; }
 inline uint32_t num_tiles(uint64_t count) { return (uint32_t)((count + tile_pairs(count) - 1) / tile_pairs(count)); }
-inline bool wide_status(uint64_t count) { return count >= (1ull << 30); }
+inline bool wide_status(uint64_t count) {
+    static const bool forced = getenv("USRT_FORCE_WIDE_STATUS") != nullptr;   // test hook: 64-bit look-back words at any size
+    return forced || count >= (1ull << 30);
+}
 inline uint64_t status_words_bytes(uint64_t count) { return (uint64_t)num_tiles(count) * kRadix * (wide_status(count) ? 8 : 4); }
 
 template <typename Cfg, typename StatusT, bool kHasValues>
