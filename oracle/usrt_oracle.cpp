@@ -588,6 +588,23 @@ void usrt_oracle_trace_rays(const uint32_t* sortedTriangleIndices, const AABB* t
     }
 }
 
+// Per-ray node-visit counts of a primary frame (analysis aid: warp-tile load balance of the GPU kernel).
+void usrt_oracle_primary_visit_counts(const uint32_t* sortedTriangleIndices, const AABB* triangleAABB,
+                                      const InternalNode* internalNodes, const LeafNode* leafNodes, const AABB* bvhData,
+                                      const Triangle* triangleData, int screenWidth, int screenHeight, float near,
+                                      float cameraFov, const float* cameraToWorld, uint32_t* visits, int threads) {
+    Scene s{sortedTriangleIndices, triangleAABB, internalNodes, leafNodes, bvhData, triangleData};
+    const uint64_t W = (uint64_t)screenWidth, n = W * (uint64_t)screenHeight;
+    parallel_for(n, threads, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t i = b; i < e; ++i) {
+            TraceCounters c{0, 0, 0, 0};
+            Ray ray = PrimaryRay((uint32_t)(i % W), (uint32_t)(i / W), screenWidth, screenHeight, near, cameraFov, cameraToWorld);
+            TraverseRay(s, ray, &c);
+            visits[i] = (uint32_t)c.boxTests;
+        }
+    });
+}
+
 // Primary-ray generation only (for tests of K6a and for feeding trace_rays with identical rays).
 void usrt_oracle_primary_rays(int screenWidth, int screenHeight, float near, float cameraFov,
                               const float* cameraToWorld, float* rays_out /* W*H*8 floats */) {

@@ -32,6 +32,18 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
     return add(add(mul(ax, bx), mul(ay, by)), mul(az, bz));
 }
 
+// One 64-byte packed node = two 256-bit loads (LDG.E.256, new on sm_100): the lanes of a warp sit on ~9
+// different nodes on average, and every load instruction pays one L1 wavefront per distinct line, so
+// halving the instruction count per node halves the LSU-pipe cost of the walk.
+struct Node8 { float4 lo, hi; };
+__device__ __forceinline__ Node8 ldg256(const float4* p) {
+    Node8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
+
 // Constants.cginc:7 -- integer literal 0x7F7FFFFF converted to float
 __device__ __forceinline__ float max_float() { return __uint_as_float(0x4EFF0000u); }
 
@@ -101,7 +113,8 @@ __device__ __forceinline__ usrt_raycast_result traverse(const TraceScene& s, con
     uint32_t index = 0;
     while (true) {
         const float4* pn = s.packed_nodes + (size_t)index * 4;
-        const float4 q0 = __ldg(pn + 0), q1 = __ldg(pn + 1), q2 = __ldg(pn + 2), q3 = __ldg(pn + 3);
+        const Node8 n01 = ldg256(pn), n23 = ldg256(pn + 2);
+        const float4 q0 = n01.lo, q1 = n01.hi, q2 = n23.lo, q3 = n23.hi;
         const uint32_t lref = __float_as_uint(q3.x), rref = __float_as_uint(q3.y);
 
         float lentry, rentry;
@@ -129,6 +142,74 @@ __device__ __forceinline__ usrt_raycast_result traverse(const TraceScene& s, con
             if (sp == 0) break;
             index = stack[--sp];
         }
+    }
+    return best;
+}
+
+// Strict mode, warp-cooperative form. The reference never culls, so the walk (which nodes are visited, in
+// which order) does not depend on any intersection result: only the ORDER in which a ray's candidate
+// triangles are tested matters (strict '<', first visited wins). The ~75-instruction Moller-Trumbore block
+// is therefore taken out of the node loop: a lane appends the leaves it reaches to a small per-lane FIFO
+// (shared memory, [slot][thread] so it is bank-conflict-free) and the warp runs one "triangle round" --
+// every lane pops its oldest pending leaf -- only when some lane's FIFO is nearly full, or at the end. In
+// the plain loop the block ran in ~2/3 of all iterations with one or two lanes active; here it runs a
+// dozen times per warp with most lanes active. Per-ray test order is unchanged, so results are identical.
+constexpr int kLeafFifo = 8;                            // entries per lane; an iteration appends at most 2
+
+__device__ __forceinline__ usrt_raycast_result traverse_strict(const TraceScene& s, const Ray& ray, bool valid,
+                                                               uint32_t (*fifo)[128]) {
+    usrt_raycast_result best;
+    best.distance = max_float();                       // Raytracing.compute:129-131
+    best.triangleIndex = 0;
+    best.uv[0] = 0.0f; best.uv[1] = 0.0f;
+    const uint32_t tid = threadIdx.x;
+
+    bool alive = valid;
+    if (alive) {                                        // node 0 is popped and its own box tested first (:135-146)
+        const float4 rmin = __ldg(reinterpret_cast<const float4*>(s.bvh));
+        const float4 rmax = __ldg(reinterpret_cast<const float4*>(s.bvh) + 1);
+        float entry;
+        alive = ray_box(rmin.x, rmin.y, rmin.z, rmax.x, rmax.y, rmax.z, ray, &entry);
+    }
+    uint32_t stack[64];                                // :133 (deferred left siblings only, <= 33 deep)
+    int sp = 0;
+    uint32_t index = 0;
+    uint32_t head = 0, count = 0;                       // FIFO state of this lane
+    while (true) {
+        if (alive) {
+            const float4* pn = s.packed_nodes + (size_t)index * 4;
+            const Node8 n01 = ldg256(pn), n23 = ldg256(pn + 2);
+            const float4 q0 = n01.lo, q1 = n01.hi, q2 = n23.lo, q3 = n23.hi;
+            const uint32_t lref = __float_as_uint(q3.x), rref = __float_as_uint(q3.y);
+            float lentry, rentry;
+            const bool lhit = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ray, &lentry);
+            const bool rhit = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ray, &rentry);
+            // left child then right child (:148-175): leaves are queued in that order
+            if (lhit && (lref & 0x80000000u)) { fifo[(head + count) & (kLeafFifo - 1)][tid] = lref & 0x7FFFFFFFu; ++count; }
+            if (rhit && (rref & 0x80000000u)) { fifo[(head + count) & (kLeafFifo - 1)][tid] = rref & 0x7FFFFFFFu; ++count; }
+            const bool lgo = lhit && !(lref & 0x80000000u), rgo = rhit && !(rref & 0x80000000u);
+            if (rgo) {
+                if (lgo) stack[sp++] = lref;
+                index = rref;
+            } else if (lgo) {
+                index = lref;
+            } else if (sp != 0) {
+                index = stack[--sp];
+            } else {
+                alive = false;
+            }
+        }
+        const bool any_alive = __any_sync(0xFFFFFFFFu, alive);
+        // triangle rounds: while some lane could overflow on its next visit, or to drain at the end
+        while (__any_sync(0xFFFFFFFFu, count > (uint32_t)(kLeafFifo - 2)) || (!any_alive && __any_sync(0xFFFFFFFFu, count != 0))) {
+            if (count != 0) {
+                const uint32_t leaf = fifo[head][tid];
+                head = (head + 1) & (kLeafFifo - 1); --count;
+                const float4* t = s.packed_tris + (size_t)leaf * 3;
+                ray_triangle(ray, __ldg(t + 0), __ldg(t + 1), __ldg(t + 2), best);
+            }
+        }
+        if (!any_alive) break;
     }
     return best;
 }
@@ -169,24 +250,31 @@ constexpr int kTileW = 16, kTileH = 8;
 template <bool kCulled>
 __global__ void __launch_bounds__(128) k_trace_primary(TraceScene scene, PrimaryParams p, usrt_raycast_result* __restrict__ out,
                                                        usrt_raycast_result* __restrict__ host_alias) {
+    __shared__ uint32_t s_fifo[kCulled ? 1 : kLeafFifo][128];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t x = blockIdx.x * kTileW + (warp & 1u) * 8u + (lane & 7u);
     const uint32_t row = blockIdx.y * kTileH + (warp >> 1) * 4u + (lane >> 3);
     uint32_t y, out_row;
+    bool valid = x < (uint32_t)p.width;
     if (p.num_shards > 0) {                                            // ray sharding: interleaved row blocks
-        if (row >= (uint32_t)p.local_rows) return;
         const uint32_t blk = row / (uint32_t)p.block_rows, in_blk = row % (uint32_t)p.block_rows;
         y = (blk * (uint32_t)p.num_shards + (uint32_t)p.shard) * (uint32_t)p.block_rows + in_blk;
         out_row = row;
-        if (y >= (uint32_t)p.height) return;
+        valid = valid && row < (uint32_t)p.local_rows && y < (uint32_t)p.height;
     } else {
         y = (uint32_t)p.y0 + row;
         out_row = y;
-        if (y >= (uint32_t)p.y1) return;
+        valid = valid && y < (uint32_t)p.y1;
     }
-    if (x >= (uint32_t)p.width) return;
-    const Ray ray = primary_ray(p, x, y);
-    const usrt_raycast_result h = traverse<kCulled>(scene, ray);
+    const Ray ray = primary_ray(p, x, y);                              // harmless for off-frame lanes
+    usrt_raycast_result h;
+    if (kCulled) {
+        if (!valid) return;
+        h = traverse<true>(scene, ray);
+    } else {
+        h = traverse_strict(scene, ray, valid, s_fifo);               // whole warps stay together (warp votes inside)
+        if (!valid) return;
+    }
     store_hit(out, (size_t)out_row * (size_t)p.width + x, h);          // frame mode: record index = y*W + x
     if (host_alias != nullptr) store_hit(host_alias, (size_t)out_row * (size_t)p.width + x, h);
 }
@@ -194,14 +282,23 @@ __global__ void __launch_bounds__(128) k_trace_primary(TraceScene scene, Primary
 template <bool kCulled>
 __global__ void __launch_bounds__(128) k_trace_rays(TraceScene scene, const float4* __restrict__ rays, uint64_t num_rays,
                                                     usrt_raycast_result* __restrict__ out) {
+    __shared__ uint32_t s_fifo[kCulled ? 1 : kLeafFifo][128];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= num_rays) return;
-    const float4 o = __ldg(rays + i * 2), d = __ldg(rays + i * 2 + 1);
+    const bool valid = i < num_rays;
+    const uint64_t j = valid ? i : 0;
+    const float4 o = __ldg(rays + j * 2), d = __ldg(rays + j * 2 + 1);
     Ray r;
     r.ox = o.x; r.oy = o.y; r.oz = o.z;
     r.dx = d.x; r.dy = d.y; r.dz = d.z;
     r.ix = __fdiv_rn(1.0f, d.x); r.iy = __fdiv_rn(1.0f, d.y); r.iz = __fdiv_rn(1.0f, d.z);
-    const usrt_raycast_result h = traverse<kCulled>(scene, r);
+    usrt_raycast_result h;
+    if (kCulled) {
+        if (!valid) return;
+        h = traverse<true>(scene, r);
+    } else {
+        h = traverse_strict(scene, r, valid, s_fifo);
+        if (!valid) return;
+    }
     store_hit(out, (size_t)i, h);
 }
 
