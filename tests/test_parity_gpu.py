@@ -258,3 +258,30 @@ def test_bvh_dump_and_reload(usrt, oracle, tmp_path):
     assert _same(c.trace_rays(rays), ref.trace_rays(rays, threads=8))
     assert _same(c.trace_primary(96, 54, cam["near"], cam["tan_half_fov"], cam["cam_to_world"]), want)
     b.close(); c.close()
+
+
+def test_many_tiny_meshes_and_ragged_ray_counts(usrt, oracle):
+    """n = 2 .. 70 triangles (single block, partial warps, every internal node spanning the one block) and ray
+    batches whose size is not a multiple of the CTA / warp size, all in one re-used context."""
+    ctx = usrt.Context(128)
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        n = int(rng.integers(2, 71))
+        tris = meshes.uniform_soup(n, seed=1000 + trial, extent=20.0, edge=8.0)
+        if trial % 5 == 0:
+            tris["b"][::2] = tris["a"][::2]                      # degenerate ones
+        if trial % 7 == 0:
+            tris[n // 2:] = tris[:n - n // 2]                    # exact duplicates -> equal Morton keys
+        ref = oracle.Scene(tris)
+        ctx.upload_triangles(tris)
+        ctx.rebuild()
+        assert np.array_equal(ctx.download(_lib.BUF_KEYS), ref.sortedMortonCodes), (trial, n)
+        assert np.array_equal(ctx.download(_lib.BUF_TRIANGLE_INDEX), ref.sortedTriangleIndices), (trial, n)
+        assert _same(ctx.download(_lib.BUF_INTERNAL_NODES, n - 1), ref.internalNodes[:n - 1]), (trial, n)
+        assert _same(ctx.download(_lib.BUF_LEAF_NODES), ref.leafNodes), (trial, n)
+        assert _same(ctx.download(_lib.BUF_BVH_DATA, n - 1), ref.bvhData[:n - 1]), (trial, n)
+        m = int(rng.integers(1, 300))
+        rays = meshes.incoherent_rays(m, seed=50 + trial, extent=25.0)
+        assert _same(ctx.trace_rays(rays), ref.trace_rays(rays)), (trial, n, m)
+    assert len(ctx.trace_rays(np.zeros((0, 8), np.float32))) == 0
+    ctx.close()
