@@ -29,6 +29,7 @@ struct usrt_context {
 
     // the seven scene buffers of MeshBufferContainer.cs:87-94 (+ ping-pong partners for keys/indices)
     uint32_t *keys = nullptr, *keys_alt = nullptr;
+    uint32_t* keys_primary = nullptr;     // the buffer Morton codes are generated into (fixed for the context)
     uint32_t *tri_index = nullptr, *tri_index_alt = nullptr;
     usrt_triangle* triangles = nullptr;
     usrt_aabb* tri_aabb = nullptr;
@@ -63,6 +64,13 @@ struct usrt_context {
     bool ev_valid = false;
     cudaEvent_t sort_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool sort_ev_valid = false;
+
+    // CUDA graph of the rebuild sequence
+    bool use_graph = true;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint32_t graph_n = 0;
+    cudaStream_t graph_stream = nullptr;
+    uint64_t graph_launches = 0;
 
     uint64_t launches = 0;
     char err[512] = {0};
@@ -202,6 +210,8 @@ int usrt_create(int device, uint32_t capacity, usrt_context** out) {
         ctx->stream = ctx->own_stream;
         const size_t c = capacity;
         CU(ctx, cudaMalloc(&ctx->keys, c * 4));
+        ctx->keys_primary = ctx->keys;
+        ctx->use_graph = getenv("USRT_NO_GRAPH") == nullptr;
         CU(ctx, cudaMalloc(&ctx->keys_alt, c * 4));
         CU(ctx, cudaMalloc(&ctx->tri_index, c * 4));
         CU(ctx, cudaMalloc(&ctx->tri_index_alt, c * 4));
@@ -240,6 +250,7 @@ int usrt_destroy(usrt_context* ctx) {
     NEED_CTX(ctx);
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     void* ptrs[] = {ctx->keys, ctx->keys_alt, ctx->tri_index, ctx->tri_index_alt, ctx->triangles, ctx->tri_aabb,
                     ctx->bvh, ctx->leaf, ctx->internal, ctx->slots, ctx->up_internal, ctx->up_leaf, ctx->packed_nodes, ctx->packed_tris,
                     ctx->scan_status, ctx->small, ctx->hits, ctx->rays, ctx->texture, ctx->shaded};
@@ -277,6 +288,7 @@ int usrt_set_world_bounds(usrt_context* ctx, float whole_min, float whole_max) {
     if (!(whole_max > whole_min)) return fail(ctx, USRT_ERR_ARG, "world bounds: max must exceed min");
     ctx->whole_min = whole_min;
     ctx->whole_max = whole_max;
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }   // kernel arguments changed
     return USRT_OK;
 }
 
@@ -426,25 +438,81 @@ int usrt_construct_bvh(usrt_context* ctx) {
     return do_bvh(ctx);
 }
 
+namespace {
+
+// The five stages enqueued back to back (RaytracingMeshDrawer.cs:34-51 without its readbacks).
+int enqueue_rebuild(usrt_context* ctx, bool timed) {
+    if (timed) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (int r = do_morton(ctx)) return r;
+    if (timed) CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (int r = do_sort(ctx)) return r;
+    if (timed) CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (int r = do_distribute(ctx)) return r;
+    if (timed) CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (int r = do_tree(ctx)) return r;
+    if (timed) CU(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (int r = do_bvh(ctx)) return r;
+    if (timed) CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+    return USRT_OK;
+}
+
+void drop_rebuild_graph(usrt_context* ctx) {
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    ctx->graph_exec = nullptr;
+    ctx->graph_n = 0;
+}
+
+}  // namespace
+
 int usrt_rebuild(usrt_context* ctx) {
     NEED_CTX(ctx);
     if (!(ctx->stage & ST_TRIS)) return fail(ctx, USRT_ERR_STATE, "rebuild: no triangles uploaded");
     if (ctx->n < 2) return fail(ctx, USRT_ERR_ARG, "rebuild: trianglesCount=%u; the reference needs >= 2 (BVH.compute:101)", ctx->n);
     if (int r = bind_device(ctx)) return r;
-    const bool t = ctx->timing;
     ctx->ev_valid = false;
-    if (t) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    if (int r = do_morton(ctx)) return r;
-    if (t) CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (int r = do_sort(ctx)) return r;
-    if (t) CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    if (int r = do_distribute(ctx)) return r;
-    if (t) CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    if (int r = do_tree(ctx)) return r;
-    if (t) CU(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
-    if (int r = do_bvh(ctx)) return r;
-    if (t) CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
-    ctx->ev_valid = t;
+    // DistributeKeys leaves keys/keys_alt swapped; start every rebuild from the same orientation so the
+    // launch sequence (and therefore a captured graph) is identical from one rebuild to the next.
+    if (ctx->keys != ctx->keys_primary) std::swap(ctx->keys, ctx->keys_alt);
+
+    if (ctx->timing || !ctx->use_graph) {            // per-stage events are recorded between launches: no graph
+        if (int r = enqueue_rebuild(ctx, ctx->timing)) return r;
+        ctx->ev_valid = ctx->timing;
+        return USRT_OK;
+    }
+    // The 12 launches + 4 memsets of a rebuild are short (the whole 1M-triangle rebuild is ~0.28 ms): replay them
+    // as one CUDA graph so the gaps between them are not paid on every rebuild. Re-captured when n, the
+    // stream, or the world box changes.
+    if (!ctx->graph_exec || ctx->graph_n != ctx->n || ctx->graph_stream != ctx->stream) {
+        drop_rebuild_graph(ctx);
+        CU(ctx, sort_scratch_reserve(ctx->sort, ctx->n, false));          // no allocation while capturing
+        const uint64_t before = ctx->launches;
+        cudaGraph_t graph = nullptr;
+        CU(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+        const int rc = enqueue_rebuild(ctx, false);
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != USRT_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            ctx->use_graph = false;                                        // fall back to plain launches for good
+            if (ctx->keys != ctx->keys_primary) std::swap(ctx->keys, ctx->keys_alt);
+            ctx->launches = before;
+            if (int r = enqueue_rebuild(ctx, false)) return r;
+            return USRT_OK;
+        }
+        ctx->graph_launches = ctx->launches - before;
+        ctx->launches = before;
+        const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail(ctx, USRT_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+        ctx->graph_n = ctx->n;
+        ctx->graph_stream = ctx->stream;
+        if (ctx->keys != ctx->keys_primary) std::swap(ctx->keys, ctx->keys_alt);   // capture advanced the host-side state
+    }
+    CU(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+    ctx->launches += ctx->graph_launches;
+    std::swap(ctx->keys, ctx->keys_alt);                                  // as do_distribute does
+    ctx->sort_ev_valid = false;
+    ctx->stage = ST_TRIS | ST_MORTON | ST_SORTED | ST_DISTRIBUTED | ST_TREE | ST_BVH;
     return USRT_OK;
 }
 
