@@ -115,3 +115,31 @@ def test_pinned_host_frame_is_written_directly_and_matches_staged_copy(usrt):
     assert pinned[40 * w:77 * w].tobytes() == pageable[40 * w:77 * w].tobytes()
     assert not pinned[:40 * w].view(np.uint8).any() and not pinned[77 * w:].view(np.uint8).any()
     ctx.close()
+
+
+def test_rebuild_graph_replay_and_legacy_stream_fallback(usrt, oracle):
+    """usrt_rebuild replays a CUDA graph; it must re-capture when n changes, survive a world-box change, and fall
+    back to plain launches on a stream that cannot be captured (torch's default stream = the legacy stream)."""
+    import torch
+    a, b = meshes.uniform_soup(5000, seed=21), meshes.uniform_soup(3000, seed=22)
+    ra, rb = oracle.Scene(a), oracle.Scene(b)
+    ctx = usrt.Context(6000)
+    ctx.upload_triangles(a)
+    for _ in range(3):
+        ctx.rebuild()
+    assert ctx.download(_lib.BUF_BVH_DATA, 4999).tobytes() == ra.bvhData[:4999].tobytes()
+    ctx.upload_triangles(b)                      # n changed -> re-capture
+    ctx.rebuild(); ctx.rebuild()
+    assert ctx.download(_lib.BUF_BVH_DATA, 2999).tobytes() == rb.bvhData[:2999].tobytes()
+    assert np.array_equal(ctx.download(_lib.BUF_KEYS), rb.sortedMortonCodes)
+    ctx.set_world_bounds(-64.0, 64.0)            # kernel argument changed -> graph dropped
+    ctx.rebuild()
+    want = oracle.Scene(b, -64.0, 64.0)
+    assert np.array_equal(ctx.download(_lib.BUF_KEYS), want.sortedMortonCodes)
+    ctx.close()
+    ctx = usrt.Context(6000)
+    ctx.use_torch_stream(torch.cuda.default_stream())     # handle 0 -> cudaStreamLegacy: not capturable
+    ctx.upload_triangles(a)
+    ctx.rebuild(); ctx.rebuild()
+    assert ctx.download(_lib.BUF_BVH_DATA, 4999).tobytes() == ra.bvhData[:4999].tobytes()
+    ctx.close()

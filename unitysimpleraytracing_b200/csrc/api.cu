@@ -487,7 +487,11 @@ int usrt_rebuild(usrt_context* ctx) {
         CU(ctx, sort_scratch_reserve(ctx->sort, ctx->n, false));          // no allocation while capturing
         const uint64_t before = ctx->launches;
         cudaGraph_t graph = nullptr;
-        CU(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();                                            // e.g. the legacy default stream cannot be captured
+            ctx->use_graph = false;
+            return enqueue_rebuild(ctx, false);
+        }
         const int rc = enqueue_rebuild(ctx, false);
         const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
         if (rc != USRT_OK || ce != cudaSuccess || !graph) {
