@@ -9,10 +9,15 @@
 // B200 design (not a port): the reference moves >= 32 B/pair/pass through a block-sorted
 // intermediate and three scan dispatches. Here one upfront kernel reads the keys once and builds
 // all four digit histograms (4 B/pair), and each pass is ONE kernel ("onesweep"): a tile of
-// BLOCK x IPT pairs is ranked with warp ballots (in place of the HLSL WavePrefixCountBits /
-// WavePrefixSum), per-digit tile offsets are chained across tiles by decoupled look-back (in place
-// of the three Scan.compute dispatches), and pairs are staged in shared memory in digit order so
-// the scatter writes coalesced runs. 16 B/pair/pass => 68 algorithmic bytes per pair.
+// BLOCK x IPT pairs is ranked warp by warp -- peer lanes with the same digit find each other through
+// one shared-memory atomicOr per key plus popc on lane masks (in place of the HLSL
+// WavePrefixCountBits / WavePrefixSum one-bit splits; a ballot loop and match.any were measured and
+// are 3x / 8x slower, tools/micro/match_bench.cu) -- per-digit tile offsets are chained across
+// tiles by decoupled look-back (in place of the three Scan.compute dispatches), and pairs are
+// staged in shared memory in digit order so the scatter writes coalesced runs.
+// 16 B/pair/pass => 68 algorithmic bytes per pair. Measured: the pass kernel is bound by the SM's
+// L1/LSU data pipe (bank conflicts of the five data-dependent shared-memory accesses per key), not
+// by HBM: profiles/r01_summary.md.
 
 #include <algorithm>
 #include <cstdlib>
@@ -24,8 +29,9 @@ namespace usrt {
 namespace {
 
 // Tile shapes. Large sorts are bound by per-key shared-memory work, so tiles are big (fewer look-back
-// steps, longer coalesced runs per digit); small sorts (the 1M-triangle rebuild) are latency-bound,
-// so tiles are small and many CTAs run at once.
+// steps, longer coalesced runs per digit). Measured alternatives at 2^26 pairs: <256,16,4> 0.374 ms,
+// <384,16,3> 0.372, <512,8,3> 0.401, <1024,8,1> 0.475 per pass against 0.360 for <512,16,2>. Very small
+// sorts (< 2^18 pairs) are pure latency and use small tiles so that more CTAs run at once.
 template <int BLOCK, int IPT, int CTAS> struct TileCfg {
     static constexpr int kBlock = BLOCK;            // threads per tile CTA
     static constexpr int kIPT = IPT;                // pairs per thread
