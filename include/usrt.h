@@ -103,6 +103,21 @@ int usrt_partition_pass_device(usrt_context* ctx, const uint32_t* src_keys, cons
                                uint32_t* dst_keys, uint32_t* dst_values, uint64_t count, int bit_offset,
                                uint32_t* histogram_out);
 
+/* Multi-GPU bucket exchange fused into the partition pass (BASELINE config 3 beyond one GPU): first the raw
+ * counts of one 8-bit digit (device, 256 x uint32), then -- once every rank knows every rank's counts and so
+ * where its pairs go -- the same stable partition pass, but with one destination base ADDRESS per digit value
+ * (device arrays of 256 x uint64): this rank's slice of the receive buffer of the GPU that owns that bucket,
+ * opened through usrt_peer_buffer_open. The scatter writes go straight over NVLink; no separate all-to-all. */
+int usrt_digit_histogram_device(usrt_context* ctx, const uint32_t* dev_keys, uint64_t count, int bit_offset, uint32_t* dev_hist_out);
+int usrt_partition_scatter_device(usrt_context* ctx, const uint32_t* src_keys, const uint32_t* src_values, uint64_t count,
+                                  int bit_offset, const uint64_t* dev_key_base, const uint64_t* dev_value_base);
+/* Device buffers that other processes on the node can map (CUDA IPC): create returns the pointer and a 64-byte
+ * handle to send to the peers; open maps a peer's buffer into this process; close with opened = 1 unmaps a
+ * peer's buffer, opened = 0 frees an own one. */
+int usrt_peer_buffer_create(usrt_context* ctx, uint64_t bytes, void** dev_ptr, unsigned char handle_out[64]);
+int usrt_peer_buffer_open(usrt_context* ctx, const unsigned char handle[64], void** dev_ptr);
+int usrt_peer_buffer_close(usrt_context* ctx, void* dev_ptr, int opened);
+
 /* ---- MeshBufferContainer.DistributeKeys() : MeshBufferContainer.cs:154-169 -------------------- */
 /* K3 -- new[0]=0; new[i]=new[i-1]+max(k[i]-k[i-1],1) in wrapping uint32 over [0, trianglesLength). */
 int usrt_distribute_keys(usrt_context* ctx);

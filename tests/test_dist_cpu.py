@@ -80,6 +80,48 @@ def test_choose_bucket_ranges():
     assert udist.choose_bucket_ranges(np.zeros(256), 2) == [0, 0, 256]
 
 
+@pytest.mark.parametrize("world", [1, 2, 5])
+@pytest.mark.parametrize("kind", ["uniform", "morton30", "onebucket"])
+def test_peer_scatter_plan_lands_a_stable_exchange(world, kind):
+    """Replay the plan of PeerSortExchange with numpy writes: every run lands in a disjoint slot, the
+    owner's buffer is source-rank-major, and a stable local sort of it gives the global stable sort."""
+    rng = np.random.default_rng(world)
+    n = 3000
+    keys = [rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32) for _ in range(world)]
+    if kind == "morton30":
+        keys = [k >> np.uint32(2) for k in keys]
+    if kind == "onebucket":
+        keys = [(k & np.uint32(0x00FFFFFF)) | np.uint32(0x21000000) for k in keys]
+    vals = [np.arange(n, dtype=np.uint32) + r * n for r in range(world)]
+    all_hist = np.stack([np.bincount(k >> 24, minlength=256) for k in keys])
+    bounds = udist.choose_bucket_ranges(all_hist.sum(0), world)
+    owner, offset, recv_total = udist.peer_scatter_plan(all_hist, bounds)
+    assert recv_total.sum() == world * n
+    bufk = [np.full(int(t), 0xDEADBEEF, np.uint32) for t in recv_total]
+    bufv = [np.zeros(int(t), np.uint32) for t in recv_total]
+    written = [np.zeros(int(t), bool) for t in recv_total]
+    for s in range(world):
+        order = np.argsort(keys[s] >> 24, kind="stable")          # the stable partition pass
+        pk, pv = keys[s][order], vals[s][order]
+        pos = 0
+        for d in range(256):
+            c = int(all_hist[s, d])
+            o, at = int(owner[d]), int(offset[s, d])
+            assert not written[o][at:at + c].any()
+            bufk[o][at:at + c], bufv[o][at:at + c] = pk[pos:pos + c], pv[pos:pos + c]
+            written[o][at:at + c] = True
+            pos += c
+    assert all(w.all() for w in written)
+    got_k, got_v = [], []
+    for o in range(world):
+        order = np.argsort(bufk[o], kind="stable")
+        got_k.append(bufk[o][order]); got_v.append(bufv[o][order])
+    all_k, all_v = np.concatenate(keys), np.concatenate(vals)
+    order = np.argsort(all_k, kind="stable")
+    assert np.array_equal(np.concatenate(got_k), all_k[order])
+    assert np.array_equal(np.concatenate(got_v), all_v[order])
+
+
 def _frame_worker(rank, world, port, W, H, block_rows, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)

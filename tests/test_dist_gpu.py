@@ -78,3 +78,55 @@ def test_dist_sort_matches_global_stable_sort(tmp_path):
     order = np.argsort(all_k, kind="stable")
     assert np.array_equal(np.concatenate([p["k"] for p in parts]), all_k[order])
     assert np.array_equal(np.concatenate([p["v"] for p in parts]), all_v[order])
+
+
+def _peer_sort_worker(rank, world, port, n, rounds, out_dir):
+    import torch
+    import torch.distributed as dist
+    from unitysimpleraytracing_b200 import dist as udist, host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ctx = host.Context(2, device=rank)
+    ex = udist.PeerSortExchange(ctx, int(n * 1.5) + 4096)
+    for it in range(rounds):                              # buffers are reused: the second round checks the fences
+        rng = np.random.default_rng(100 * it + 7 + rank)
+        keys = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+        keys[::5] = keys[0]
+        if it == 1:
+            keys &= np.uint32(0x3FFFFFFF)                  # Morton-like: top byte < 64
+        vals = (np.arange(n) + rank * n).astype(np.uint32)
+        k, v = ex.sort(torch.from_numpy(keys.view(np.int32)).to(dev), torch.from_numpy(vals.view(np.int32)).to(dev))
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, "p%d_%d.npz" % (it, rank)), k=k.cpu().numpy().view(np.uint32),
+                 v=v.cpu().numpy().view(np.uint32), ik=keys, iv=vals)
+    ex.close()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def _check_peer_sort(tmp_path, world, rounds):
+    for it in range(rounds):
+        parts = [np.load(tmp_path / ("p%d_%d.npz" % (it, r))) for r in range(world)]
+        all_k = np.concatenate([p["ik"] for p in parts]); all_v = np.concatenate([p["iv"] for p in parts])
+        order = np.argsort(all_k, kind="stable")
+        assert np.array_equal(np.concatenate([p["k"] for p in parts]), all_k[order])
+        assert np.array_equal(np.concatenate([p["v"] for p in parts]), all_v[order])
+
+
+@pytest.mark.parametrize("n", [1000, (1 << 20) + 77])
+def test_peer_scatter_sort_single_rank(tmp_path, n):
+    """world = 1: the per-digit-address partition kernel and the landing plan, on one GPU."""
+    import torch.multiprocessing as mp
+    mp.spawn(_peer_sort_worker, args=(1, _free_port(), n, 2, str(tmp_path)), nprocs=1, join=True)
+    _check_peer_sort(tmp_path, 1, 2)
+
+
+def test_peer_scatter_sort_matches_global_stable_sort(tmp_path):
+    """The partition pass writing into the other GPU's receive buffer over NVLink (CUDA IPC)."""
+    _need_gpus(2)
+    import torch.multiprocessing as mp
+    world, n = 2, (1 << 20) + 13
+    mp.spawn(_peer_sort_worker, args=(world, _free_port(), n, 2, str(tmp_path)), nprocs=world, join=True)
+    _check_peer_sort(tmp_path, world, 2)

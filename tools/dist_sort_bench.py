@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 from unitysimpleraytracing_b200 import host, dist as udist
 
-ap = argparse.ArgumentParser(); ap.add_argument("--log2", type=int, nargs="*", default=[28]); ap.add_argument("--iters", type=int, default=3)
+ap = argparse.ArgumentParser(); ap.add_argument("--log2", type=int, nargs="*", default=[28]); ap.add_argument("--iters", type=int, default=3); ap.add_argument("--exchange", choices=["nccl", "peer"], default="nccl")
 a = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
@@ -21,13 +21,14 @@ for lg in a.log2:
     k0 = torch.randint(-2 ** 31, 2 ** 31 - 1, (n,), dtype=torch.int32, device=dev, generator=g)
     v0 = torch.arange(n, dtype=torch.int32, device=dev) + rank * n
     times = []
+    ex = udist.PeerSortExchange(ctx, int(n * 1.25) + 4096) if (world > 1 and a.exchange == "peer") else None
     for it in range(a.iters + 1):
         k = k0.clone(); v = v0.clone()
         torch.cuda.synchronize(); 
         if world > 1: dist.barrier()
         torch.cuda.synchronize(); t0 = time.perf_counter()
         if world > 1:
-            rk, rv = udist.dist_sort_pairs(k, v, ctx=ctx)
+            rk, rv = ex.sort(k, v) if ex else udist.dist_sort_pairs(k, v, ctx=ctx)
         else:
             ctx.use_torch_stream(); ctx.sort_pairs_device(k.data_ptr(), v.data_ptr(), n); rk, rv = k, v
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
@@ -48,9 +49,10 @@ for lg in a.log2:
         glob, cnt = True, torch.tensor([rk.numel()])
     if rank == 0:
         best = min(times)
-        print("dist sort 2^%d pairs on %d GPU(s): %.3f ms  %.0f Mkeys/s  locally sorted=%s globally ordered=%s total=%d"
+        print("dist sort [" + a.exchange + "] 2^%d pairs on %d GPU(s): %.3f ms  %.0f Mkeys/s  locally sorted=%s globally ordered=%s total=%d"
               % (lg, world, best * 1e3, (1 << lg) / best / 1e6, ok, glob, int(cnt.item())), flush=True)
     del k0, v0, rk, rv
+    if ex: ex.close()
     torch.cuda.empty_cache()
 ctx.close()
 dist.destroy_process_group()

@@ -34,6 +34,11 @@ SIGNATURES = {
     "usrt_sort_pairs_device": (_c.c_int, [_P, _P, _P, _c.c_uint64]),
     "usrt_sort_pairs_host": (_c.c_int, [_P, _P, _P, _c.c_uint64]),
     "usrt_partition_pass_device": (_c.c_int, [_P, _P, _P, _P, _P, _c.c_uint64, _c.c_int, _P]),
+    "usrt_digit_histogram_device": (_c.c_int, [_P, _P, _c.c_uint64, _c.c_int, _P]),
+    "usrt_partition_scatter_device": (_c.c_int, [_P, _P, _P, _c.c_uint64, _c.c_int, _P, _P]),
+    "usrt_peer_buffer_create": (_c.c_int, [_P, _c.c_uint64, _c.POINTER(_P), _P]),
+    "usrt_peer_buffer_open": (_c.c_int, [_P, _P, _c.POINTER(_P)]),
+    "usrt_peer_buffer_close": (_c.c_int, [_P, _P, _c.c_int]),
     "usrt_distribute_keys": (_c.c_int, [_P]),
     "usrt_construct_tree": (_c.c_int, [_P]),
     "usrt_construct_bvh": (_c.c_int, [_P]),

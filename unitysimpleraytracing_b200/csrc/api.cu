@@ -415,6 +415,61 @@ int usrt_partition_pass_device(usrt_context* ctx, const uint32_t* src_keys, cons
     return USRT_OK;
 }
 
+int usrt_digit_histogram_device(usrt_context* ctx, const uint32_t* dev_keys, uint64_t count, int bit_offset, uint32_t* dev_hist_out) {
+    NEED_CTX(ctx);
+    if (bit_offset < 0 || bit_offset > 24 || (bit_offset & 7) || !dev_hist_out || (count && !dev_keys) || count >= (1ull << 32))
+        return fail(ctx, USRT_ERR_ARG, "digit_histogram: bad arguments");
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, digit_histogram(dev_keys, count, bit_offset, dev_hist_out, ctx->sort, ctx->stream, &ctx->launches));
+    return USRT_OK;
+}
+
+int usrt_partition_scatter_device(usrt_context* ctx, const uint32_t* src_keys, const uint32_t* src_values, uint64_t count,
+                                  int bit_offset, const uint64_t* dev_key_base, const uint64_t* dev_value_base) {
+    NEED_CTX(ctx);
+    if (bit_offset < 0 || bit_offset > 24 || (bit_offset & 7) || !dev_key_base || !dev_value_base ||
+        (count && (!src_keys || !src_values)) || count >= (1ull << 30))
+        return fail(ctx, USRT_ERR_ARG, "partition_scatter: bad arguments");
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, partition_scatter(src_keys, src_values, count, bit_offset, reinterpret_cast<const unsigned long long*>(dev_key_base),
+                              reinterpret_cast<const unsigned long long*>(dev_value_base), ctx->sort, ctx->stream, &ctx->launches));
+    return USRT_OK;
+}
+
+int usrt_peer_buffer_create(usrt_context* ctx, uint64_t bytes, void** dev_ptr, unsigned char handle_out[64]) {
+    NEED_CTX(ctx);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!dev_ptr || !handle_out || bytes == 0) return fail(ctx, USRT_ERR_ARG, "peer_buffer_create: bad arguments");
+    if (int r = bind_device(ctx)) return r;
+    void* p = nullptr;
+    CU(ctx, cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(ctx, USRT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle_out, &h, 64);
+    *dev_ptr = p;
+    return USRT_OK;
+}
+
+int usrt_peer_buffer_open(usrt_context* ctx, const unsigned char handle[64], void** dev_ptr) {
+    NEED_CTX(ctx);
+    if (!handle || !dev_ptr) return fail(ctx, USRT_ERR_ARG, "peer_buffer_open: bad arguments");
+    if (int r = bind_device(ctx)) return r;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return USRT_OK;
+}
+
+int usrt_peer_buffer_close(usrt_context* ctx, void* dev_ptr, int opened) {
+    NEED_CTX(ctx);
+    if (!dev_ptr) return USRT_OK;
+    if (int r = bind_device(ctx)) return r;
+    if (opened) CU(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    else CU(ctx, cudaFree(dev_ptr));
+    return USRT_OK;
+}
+
 int usrt_distribute_keys(usrt_context* ctx) {
     NEED_CTX(ctx);
     if (!(ctx->stage & ST_SORTED)) return fail(ctx, USRT_ERR_STATE, "distribute_keys: keys not sorted (call usrt_sort)");

@@ -155,11 +155,15 @@ template <typename Cfg, bool kHasValues> struct PassSmem {
     static constexpr int kTotal = Cfg::kMatchBytes + kPairBytes + kRadix * 4 + Cfg::kWarps * 4 + 16;
 };
 
-template <typename Cfg, typename StatusT, bool kHasValues>
+// kPeer: the multi-GPU bucket exchange. Instead of one output array, every digit has its own base address
+// (key_ptrs[d] / val_ptrs[d], this rank's slice of the receive buffer of the GPU that owns bucket d, mapped
+// through CUDA IPC): the stable scatter of the pass IS the all-to-all, written straight over NVLink.
+template <typename Cfg, typename StatusT, bool kHasValues, bool kPeer = false>
 __global__ void __launch_bounds__(Cfg::kBlock, Cfg::kCtasPerSM)
 k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ digit_base /* [256] */,
-           uint32_t* __restrict__ tile_counter, StatusT* __restrict__ status /* [tiles][256], zeroed */) {
+           uint32_t* __restrict__ tile_counter, StatusT* __restrict__ status /* [tiles][256], zeroed */,
+           const unsigned long long* __restrict__ key_ptrs = nullptr, const unsigned long long* __restrict__ val_ptrs = nullptr) {
     using ST = StatusTraits<StatusT>;
     constexpr int kBlock = Cfg::kBlock, kIPT = Cfg::kIPT, kTile = Cfg::kTile, kWarps = Cfg::kWarps;
     constexpr int kMatchBytes = Cfg::kMatchBytes;
@@ -307,7 +311,7 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
             }
             ST::store(my_status, ST::kPrefix | (StatusT)(exclusive + count));
         }
-        s_global_off[d] = digit_base[d] + exclusive - tile_start;   // wraps mod 2^32 by design
+        s_global_off[d] = (kPeer ? 0u : digit_base[d]) + exclusive - tile_start;   // wraps mod 2^32 by design
     }
     __syncthreads();
 
@@ -318,9 +322,15 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
         if (p < valid) {
             if (kHasValues) {
                 const uint2 kv = s_pairs[p];
-                const uint32_t dst = s_global_off[(kv.x >> shift) & 255u] + p;
-                keys_out[dst] = kv.x;
-                vals_out[dst] = kv.y;
+                const uint32_t dg = (kv.x >> shift) & 255u;
+                const uint32_t dst = s_global_off[dg] + p;
+                if (kPeer) {
+                    reinterpret_cast<uint32_t*>(__ldg(key_ptrs + dg))[dst] = kv.x;
+                    reinterpret_cast<uint32_t*>(__ldg(val_ptrs + dg))[dst] = kv.y;
+                } else {
+                    keys_out[dst] = kv.x;
+                    vals_out[dst] = kv.y;
+                }
             } else {
                 const uint32_t k = s_keys[p];
                 keys_out[s_global_off[(k >> shift) & 255u] + p] = k;
@@ -456,6 +466,45 @@ cudaError_t partition_pass(const uint32_t* src_keys, const uint32_t* src_vals, u
         e = run_pass<uint32_t>(src_keys, src_vals, dst_keys, dst_vals, count, bit_offset, s.hist + pass * kRadix, counters, st, stream);
     if (launches) *launches += 3;
     return e;
+}
+
+// Raw counts of one digit (no scan): the first half of the multi-GPU bucket exchange.
+cudaError_t digit_histogram(const uint32_t* keys, uint64_t count, int bit_offset, uint32_t* hist_out, SortScratch& s,
+                            cudaStream_t stream, uint64_t* launches) {
+    cudaError_t e;
+    if ((e = sort_scratch_reserve(s, std::max<uint64_t>(count, 1), false)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.hist, 0, kSortPasses * kRadix * 4, stream)) != cudaSuccess) return e;
+    if (count) {
+        k_histogram<<<histogram_grid(count), kHistThreads, kHistSmemBytes, stream>>>(keys, count, s.hist);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (launches) *launches += 1;
+    }
+    return cudaMemcpyAsync(hist_out, s.hist + (bit_offset / kRadixBits) * kRadix, kRadix * 4, cudaMemcpyDeviceToDevice, stream);
+}
+
+// The stable partition pass with one destination base address per digit (peer memory allowed).
+cudaError_t partition_scatter(const uint32_t* src_keys, const uint32_t* src_vals, uint64_t count, int bit_offset,
+                              const unsigned long long* key_ptrs, const unsigned long long* val_ptrs, SortScratch& s,
+                              cudaStream_t stream, uint64_t* launches) {
+    if (count == 0) return cudaSuccess;
+    cudaError_t e;
+    if ((e = sort_scratch_reserve(s, count, false)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.status, 0, kHeaderWords * 4 + status_words_bytes(count), stream)) != cudaSuccess) return e;
+    uint32_t* counters = static_cast<uint32_t*>(s.status);
+    uint32_t* st = reinterpret_cast<uint32_t*>(static_cast<char*>(s.status) + kHeaderWords * 4);
+    if (count < kSmallSortLimit) {
+        constexpr int smem = PassSmem<SmallTile, true>::kTotal;
+        cudaFuncSetAttribute(k_onesweep<SmallTile, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        k_onesweep<SmallTile, uint32_t, true, true><<<num_tiles(count), SmallTile::kBlock, smem, stream>>>(
+            src_keys, src_vals, nullptr, nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, key_ptrs, val_ptrs);
+    } else {
+        constexpr int smem = PassSmem<BigTile, true>::kTotal;
+        cudaFuncSetAttribute(k_onesweep<BigTile, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        k_onesweep<BigTile, uint32_t, true, true><<<num_tiles(count), BigTile::kBlock, smem, stream>>>(
+            src_keys, src_vals, nullptr, nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, key_ptrs, val_ptrs);
+    }
+    if (launches) *launches += 1;
+    return cudaGetLastError();
 }
 
 }  // namespace usrt

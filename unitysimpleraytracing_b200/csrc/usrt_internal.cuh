@@ -38,6 +38,13 @@ cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint3
 cudaError_t partition_pass(const uint32_t* src_keys, const uint32_t* src_vals, uint32_t* dst_keys, uint32_t* dst_vals,
                            uint64_t count, int bit_offset, uint32_t* histogram_out, SortScratch& scratch,
                            cudaStream_t stream, uint64_t* launches);
+// multi-GPU bucket exchange: raw digit counts, then the partition pass scattering straight into per-digit
+// destination addresses (peer memory over NVLink)
+cudaError_t digit_histogram(const uint32_t* keys, uint64_t count, int bit_offset, uint32_t* hist_out, SortScratch& scratch,
+                            cudaStream_t stream, uint64_t* launches);
+cudaError_t partition_scatter(const uint32_t* src_keys, const uint32_t* src_vals, uint64_t count, int bit_offset,
+                              const unsigned long long* key_ptrs, const unsigned long long* val_ptrs, SortScratch& scratch,
+                              cudaStream_t stream, uint64_t* launches);
 cudaError_t sort_scratch_reserve(SortScratch& scratch, uint64_t count, bool need_alt);
 void sort_scratch_free(SortScratch& scratch);
 

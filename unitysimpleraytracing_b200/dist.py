@@ -8,7 +8,9 @@ gloo for the CPU tests of the host logic). Only the two places where the path sh
  (b) sorts of >= 2^28 pairs -- keys are split into MSD buckets (top byte), bucket ranges of roughly
      equal mass are assigned to ranks, pairs are exchanged all-to-all and sorted locally. Global order
      = rank order; stable across ranks because sources are concatenated in rank order and both the
-     bucket split and the local sort are stable.
+     bucket split and the local sort are stable. Two exchanges: `dist_sort_pairs` (local split, then
+     NCCL all-to-all) and `PeerSortExchange` (the split pass itself scatters into the owners' receive
+     buffers through NVLink peer memory -- one kernel is both the split and the all-to-all).
 
 Morton / DistributeKeys / tree / refit do not shard without a global exchange: replicas only.
 
@@ -164,3 +166,109 @@ def dist_sort_pairs(keys_t, vals_t, group=None, local_partition=None, local_sort
     # 5. stable local sort of what arrived (sources are concatenated in rank order)
     local_sort(rk, rv)
     return rk, rv
+
+
+def peer_scatter_plan(all_hist, bounds):
+    """Where every (source rank, top-byte value) run lands. all_hist: (world, 256) counts; bounds from
+    choose_bucket_ranges. Returns (owner[256], offset[world][256], recv_total[world]): source s writes its
+    run of digit d at element `offset[s][d]` of rank `owner[d]`'s receive buffer. The layout inside an owner
+    is source-rank-major, digits ascending within a source -- the order the all-to-all of dist_sort_pairs
+    produces -- so a stable local sort of the buffer gives the globally stable result."""
+    h = np.asarray(all_hist, np.int64)
+    world = h.shape[0]
+    owner = np.zeros(256, np.int64)
+    for r in range(world):
+        owner[bounds[r]:bounds[r + 1]] = r
+    offset = np.zeros((world, 256), np.int64)
+    recv_total = np.zeros(world, np.int64)
+    for o in range(world):
+        lo, hi = bounds[o], bounds[o + 1]
+        base = 0
+        for s_ in range(world):
+            run = h[s_, lo:hi]
+            offset[s_, lo:hi] = base + np.concatenate([[0], np.cumsum(run)[:-1]]) if hi > lo else 0
+            base += int(run.sum())
+        recv_total[o] = base
+    return owner, offset, recv_total
+
+
+class _DeviceView:
+    """A library-owned device range as a __cuda_array_interface__ object (for torch.as_tensor)."""
+
+    def __init__(self, ptr, count, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerSortExchange:
+    """Multi-GPU sort whose bucket exchange is fused into the partition kernel (usrt.h:
+    usrt_partition_scatter_device). Every rank owns a receive buffer of `capacity` pairs, mapped into every
+    other rank through CUDA IPC at construction. sort():
+      1. top-byte counts of the local keys (one kernel), all-gathered (world x 256 counters);
+      2. identical bucket ranges + landing offsets on every rank (peer_scatter_plan);
+      3. ONE partition pass that writes each pair straight into its owner's receive buffer over NVLink;
+      4. a one-element all-reduce as the "all scatters landed" fence; 5. stable local 4-pass sort.
+    Collectives carry only counters; the pairs never pass through NCCL."""
+
+    def __init__(self, ctx, capacity, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.group, self.capacity = ctx, group, int(capacity)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.own_ptr, handle = ctx.peer_buffer_create(self.capacity * 8)       # keys | values
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy().reshape(self.world, 64)
+        self.peer_ptr = [self.own_ptr if r == self.rank else ctx.peer_buffer_open(allh[r].tobytes())
+                         for r in range(self.world)]
+        self._fence = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._hist = torch.zeros(256, dtype=torch.int32, device=self.device)
+        self._all_hist = torch.empty(self.world * 256, dtype=torch.int32, device=self.device)
+        self._ptrs_host = torch.empty(512, dtype=torch.int64).pin_memory()
+        self._ptrs = torch.empty(512, dtype=torch.int64, device=self.device)
+
+    def sort(self, keys_t, vals_t):
+        """-> (keys, vals): this rank's contiguous chunk of the global stable sort, as views of the receive
+        buffer (valid until the next sort())."""
+        import torch
+        import torch.distributed as dist
+        n = keys_t.numel()
+        ctx = self.ctx
+        ctx.use_torch_stream()
+        ctx.digit_histogram_device(keys_t.data_ptr(), n, 24, self._hist.data_ptr())
+        # also the "receive buffers are free again" barrier: a rank gets here only after its previous local sort
+        dist.all_gather_into_tensor(self._all_hist, self._hist, group=self.group)
+        all_hist = self._all_hist.cpu().numpy().reshape(self.world, 256)
+        bounds = choose_bucket_ranges(all_hist.sum(0, dtype=np.int64), self.world)
+        owner, offset, recv_total = peer_scatter_plan(all_hist, bounds)
+        if int(recv_total.max()) > self.capacity:
+            raise ValueError(f"receive buffer of {self.capacity} pairs too small for {int(recv_total.max())}")
+        base = np.asarray(self.peer_ptr, np.int64)[owner]
+        tbl = self._ptrs_host.numpy()
+        tbl[:256] = base + 4 * offset[self.rank]
+        tbl[256:] = base + 4 * (self.capacity + offset[self.rank])
+        self._ptrs.copy_(self._ptrs_host, non_blocking=True)
+        ctx.partition_scatter_device(keys_t.data_ptr(), vals_t.data_ptr(), n, 24, self._ptrs.data_ptr(),
+                                     self._ptrs.data_ptr() + 256 * 8)
+        dist.all_reduce(self._fence, group=self.group)           # every rank's scatter has completed
+        m = int(recv_total[self.rank])
+        kptr, vptr = self.own_ptr, self.own_ptr + 4 * self.capacity
+        if m:
+            ctx.sort_pairs_device(kptr, vptr, m)
+        if m == 0:
+            return keys_t.new_empty(0), vals_t.new_empty(0)
+        rk = torch.as_tensor(_DeviceView(kptr, m), device=self.device)
+        rv = torch.as_tensor(_DeviceView(vptr, m), device=self.device)
+        return rk, rv
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        for r, p in enumerate(self.peer_ptr):
+            if r != self.rank and p:
+                self.ctx.peer_buffer_close(p, True)
+        if self.own_ptr:
+            self.ctx.peer_buffer_close(self.own_ptr, False)
+        self.peer_ptr, self.own_ptr = [], 0

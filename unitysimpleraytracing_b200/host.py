@@ -125,6 +125,31 @@ class Context:
                                                          vp(dst_keys), vp(dst_vals) if dst_vals else None, count,
                                                          bit_offset, vp(hist_ptr) if hist_ptr else None))
 
+    def digit_histogram_device(self, keys_ptr, count, bit_offset, hist_ptr):
+        vp = ctypes.c_void_p
+        self._check(self._lib.usrt_digit_histogram_device(self._h, vp(keys_ptr), count, bit_offset, vp(hist_ptr)))
+
+    def partition_scatter_device(self, src_keys, src_vals, count, bit_offset, key_base_ptr, value_base_ptr):
+        vp = ctypes.c_void_p
+        self._check(self._lib.usrt_partition_scatter_device(self._h, vp(src_keys), vp(src_vals), count, bit_offset,
+                                                            vp(key_base_ptr), vp(value_base_ptr)))
+
+    def peer_buffer_create(self, nbytes):
+        """-> (device pointer, 64-byte IPC handle) of a buffer other processes on the node can map."""
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        self._check(self._lib.usrt_peer_buffer_create(self._h, nbytes, ctypes.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def peer_buffer_open(self, handle):
+        ptr = ctypes.c_void_p()
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self._lib.usrt_peer_buffer_open(self._h, buf, ctypes.byref(ptr)))
+        return ptr.value
+
+    def peer_buffer_close(self, ptr, opened):
+        self._check(self._lib.usrt_peer_buffer_close(self._h, ctypes.c_void_p(ptr), 1 if opened else 0))
+
     def distribute_keys(self):
         self._check(self._lib.usrt_distribute_keys(self._h))
 
