@@ -176,19 +176,14 @@ def peer_scatter_plan(all_hist, bounds):
     produces -- so a stable local sort of the buffer gives the globally stable result."""
     h = np.asarray(all_hist, np.int64)
     world = h.shape[0]
-    owner = np.zeros(256, np.int64)
-    for r in range(world):
-        owner[bounds[r]:bounds[r + 1]] = r
-    offset = np.zeros((world, 256), np.int64)
-    recv_total = np.zeros(world, np.int64)
-    for o in range(world):
-        lo, hi = bounds[o], bounds[o + 1]
-        base = 0
-        for s_ in range(world):
-            run = h[s_, lo:hi]
-            offset[s_, lo:hi] = base + np.concatenate([[0], np.cumsum(run)[:-1]]) if hi > lo else 0
-            base += int(run.sum())
-        recv_total[o] = base
+    b = np.asarray(bounds, np.int64)
+    owner = np.repeat(np.arange(world), np.diff(b))                       # [256]
+    C = np.zeros((world, 257), np.int64)
+    np.cumsum(h, axis=1, out=C[:, 1:])                                    # C[s][j] = sum of h[s][:j]
+    T = C[:, b[1:]] - C[:, b[:-1]]                                        # T[s][o]: pairs source s sends to owner o
+    before = np.cumsum(T, axis=0) - T                                     # from the lower-ranked sources
+    offset = before[:, owner] + C[:, :256] - C[:, b[owner]]
+    recv_total = T.sum(axis=0)
     return owner, offset, recv_total
 
 
