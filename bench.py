@@ -205,17 +205,32 @@ def run_ours(args):
 
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
+    # N > 1: every rank must end each step holding all N frames. exchange "peer" (default): the trace kernel
+    # stores each hit record into every rank's frame buffer over NVLink peer memory (usrt_set_hit_mirrors),
+    # a one-element all-reduce on a side stream is the "frame complete" fence; "nccl": trace, then all-gather.
+    exchange = os.environ.get("USRT_BENCH_EXCHANGE", "peer") if world > 1 else None
     comm_stream = torch.cuda.Stream() if world > 1 else None
-    gathered = [torch.empty(world * rays * 4, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
-    hit_copy = [torch.empty(rays * 4, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    peer = None
+    if exchange == "peer":
+        from unitysimpleraytracing_b200 import dist as udist
+        peer = udist.PeerFrameExchange(ctx, rays, buffers=2)
+    gathered = [torch.empty(world * rays * 4, dtype=torch.float32, device=dev) for _ in range(2)] if exchange == "nccl" else None
+    hit_copy = [torch.empty(rays * 4, dtype=torch.float32, device=dev) for _ in range(2)] if exchange == "nccl" else None
 
     def step(i, ev0=None, ev1=None):
         flush.fill_(i & 0xFF)                                           # L2 flush, outside the event pair
         if ev0 is not None:
             ev0.record(stream)
         ctx.rebuild()
+        if peer is not None:
+            stream.wait_stream(comm_stream)        # fence of step i-1 passed: every rank is done with frame buffer i&1
+            peer.select(i & 1)
         ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=False)
-        if world > 1:
+        if peer is not None:
+            comm_stream.wait_stream(stream)
+            with torch.cuda.stream(comm_stream):
+                peer.fence()
+        elif world > 1:
             # hand the frame to the comm stream: copy out of the context's hit buffer, then all-gather
             # there while the next step computes here
             ptr, cnt = ctx.hits_device()
@@ -262,6 +277,9 @@ def run_ours(args):
             sort_acc.setdefault(k, []).append(v)
     ctx.enable_stage_timing(False)
     barrier()
+    if peer is not None:
+        peer.close()                       # clears the mirrors: the legs below are single-GPU
+        barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = sum(step_ms)
     if world > 1:
@@ -374,7 +392,7 @@ def run_ours(args):
             "config": {"workload": "configs[1]: 1,048,576-tri sphere+height-field, full rebuild + 1920x1080 primary rays",
                        "triangles": int(n), "rays_per_step_per_gpu": rays, "trace_mode": "strict (reference visiting order, no culling)",
                        "l2": "flushed between timed steps (512 MiB write) and the scene (357 MB) exceeds the 126 MB L2",
-                       "parallelism": "1 GPU" if world == 1 else "ray-sharded x%d, replicated BVH, all-gather of hit records overlapped" % world},
+                       "parallelism": "1 GPU" if world == 1 else "ray-sharded x%d, replicated BVH, %s" % (world, "hit records stored to every rank by the trace kernel over NVLink peer memory" if exchange == "peer" else "all-gather of hit records overlapped")},
             "stages_ms": stages,
             "trace_mrays_s": rays / (trace_ms * 1e-3) / 1e6,
             "build_ms": stages["total"],

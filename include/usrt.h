@@ -139,6 +139,12 @@ int usrt_last_rebuild_ms(usrt_context* ctx, float out_ms[6]);
  * kernel group, in ms: histogram+scan, pass bitOffset 0, 8, 16, 24, total. Synchronises. */
 int usrt_last_sort_ms(usrt_context* ctx, float out_ms[6]);
 
+/* Ray-sharded frames without a separate all-gather: up to 8 extra DEVICE destinations (frame slots of this and
+ * of peer GPUs, the latter opened with usrt_peer_buffer_open) that usrt_trace_primary / usrt_trace_primary_sharded write every hit record
+ * to as well, at the same record index, by the trace kernel's own stores over NVLink. count = 0 clears. The
+ * caller fences across ranks (e.g. a one-element all-reduce) before reading a peer-written slot. */
+int usrt_set_hit_mirrors(usrt_context* ctx, int count, void* const* dev_ptrs);
+
 /* ---- Dispatch(Raytracing) : RaytracingMeshDrawer.cs:76-84, Raytracing.compute:105-176 ---------- */
 /* K6 -- one hit record per pixel, index y*width + x, row 0 = most negative camera-space y.
  * near = _ProjectionParams.y; tan_half_fov = tan(fovDeg*Deg2Rad/2) (RaytracingMeshDrawer.cs:80);

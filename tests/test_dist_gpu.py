@@ -19,7 +19,7 @@ def _need_gpus(k):
         pytest.skip("needs %d GPUs, %d visible" % (k, torch.cuda.device_count()))
 
 
-def _ray_worker(rank, world, port, out_dir):
+def _ray_worker(rank, world, port, out_dir, exchange="peer"):
     import torch
     import torch.distributed as dist
     from unitysimpleraytracing_b200 import dist as udist, meshes
@@ -28,19 +28,23 @@ def _ray_worker(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     tris = meshes.scene_c1()
     cam = meshes.SCENE_SOUP_CAMERA
-    d = udist.RayShardedDrawer(tris, rank, world).Awake()
+    d = udist.RayShardedDrawer(tris, rank, world, exchange=exchange).Awake()
+    d.Update(160, 90, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])       # buffers are re-made / reused
+    frame = d.Update(320, 180, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
     frame = d.Update(320, 180, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
     np.save(os.path.join(out_dir, "frame%d.npy" % rank), frame)
     d.OnDestroy()
     dist.destroy_process_group()
 
 
-def test_ray_sharded_frame_matches_oracle(tmp_path, oracle):
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_ray_sharded_frame_matches_oracle(tmp_path, oracle, exchange):
+    """peer: the trace kernel stores every record into both GPUs' frames (NVLink peer memory); nccl: all-gather."""
     _need_gpus(2)
     import torch.multiprocessing as mp
     from unitysimpleraytracing_b200 import meshes
     world = 2
-    mp.spawn(_ray_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_ray_worker, args=(world, _free_port(), str(tmp_path), exchange), nprocs=world, join=True)
     cam = meshes.SCENE_SOUP_CAMERA
     want = oracle.Scene(meshes.scene_c1()).trace_primary(320, 180, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], threads=8)
     for r in range(world):

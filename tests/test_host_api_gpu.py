@@ -117,6 +117,40 @@ def test_pinned_host_frame_is_written_directly_and_matches_staged_copy(usrt):
     ctx.close()
 
 
+def test_hit_mirrors_receive_every_record(usrt):
+    """usrt_set_hit_mirrors: the trace kernel stores each record to up to 8 more device frames (peer GPUs' slots
+    in the multi-GPU drawer; plain device buffers here), together with the zero-copy pinned host frame."""
+    import torch
+    tris = meshes.scene_c1(); cam = meshes.SCENE_SOUP_CAMERA
+    ctx = usrt.Context(len(tris)); ctx.upload_triangles(tris); ctx.rebuild()
+    w, h = 200, 77
+    want = ctx.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    mirrors = [torch.zeros(w * h * 4, dtype=torch.float32, device="cuda") for _ in range(8)]
+    ctx.set_hit_mirrors([m.data_ptr() for m in mirrors])
+    pinned_t = torch.zeros(w * h * 16, dtype=torch.uint8).pin_memory()
+    ctx.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], out=pinned_t.numpy().view(want.dtype))
+    assert pinned_t.numpy().tobytes() == want.tobytes()
+    for m in mirrors:
+        assert m.cpu().numpy().tobytes() == want.tobytes()
+    # sharded call: same compact layout in the mirrors as in the primary output
+    for m in mirrors:
+        m.fill_(7.0)
+    ctx.set_hit_mirrors([m.data_ptr() for m in mirrors[:3]])
+    ctx.trace_primary_sharded(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], 8, 1, 3)
+    ptr, cnt = ctx.hits_device()
+    ctx.sync()
+    own = torch.zeros(cnt * 4, dtype=torch.float32, device="cuda")
+    ctx.trace_primary_sharded(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], 8, 1, 3, dev_out=own.data_ptr())
+    ctx.sync()
+    for m in mirrors[:3]:
+        assert m[:cnt * 4].cpu().numpy().tobytes() == own.cpu().numpy().tobytes()
+    assert float(mirrors[3][0]) == 7.0                      # not a mirror any more
+    with pytest.raises(_lib.UsrtError):
+        ctx.set_hit_mirrors([1] * 9)
+    ctx.set_hit_mirrors([])
+    ctx.close()
+
+
 def test_rebuild_graph_replay_and_legacy_stream_fallback(usrt, oracle):
     """usrt_rebuild replays a CUDA graph; it must re-capture when n changes, survive a world-box change, and fall
     back to plain launches on a stream that cannot be captured (torch's default stream = the legacy stream)."""

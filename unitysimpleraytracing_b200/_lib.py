@@ -39,6 +39,7 @@ SIGNATURES = {
     "usrt_peer_buffer_create": (_c.c_int, [_P, _c.c_uint64, _c.POINTER(_P), _P]),
     "usrt_peer_buffer_open": (_c.c_int, [_P, _P, _c.POINTER(_P)]),
     "usrt_peer_buffer_close": (_c.c_int, [_P, _P, _c.c_int]),
+    "usrt_set_hit_mirrors": (_c.c_int, [_P, _c.c_int, _c.POINTER(_P)]),
     "usrt_distribute_keys": (_c.c_int, [_P]),
     "usrt_construct_tree": (_c.c_int, [_P]),
     "usrt_construct_bvh": (_c.c_int, [_P]),

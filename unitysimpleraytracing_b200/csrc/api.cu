@@ -53,6 +53,7 @@ struct usrt_context {
     float4* rays = nullptr;
     uint64_t rays_capacity = 0;
     int trace_mode = 0;
+    HitMirrors mirrors{};             // usrt_set_hit_mirrors: peer GPUs' frame slots
     // shading epilogue
     float4* texture = nullptr;
     int tex_w = 0, tex_h = 0;
@@ -610,6 +611,18 @@ int usrt_set_trace_mode(usrt_context* ctx, int mode) {
     return USRT_OK;
 }
 
+int usrt_set_hit_mirrors(usrt_context* ctx, int count, void* const* dev_ptrs) {
+    NEED_CTX(ctx);
+    if (count < 0 || count > kMaxHitMirrors - 1 || (count && !dev_ptrs))
+        return fail(ctx, USRT_ERR_ARG, "set_hit_mirrors: count must be 0..%d", kMaxHitMirrors - 1);
+    for (int i = 0; i < count; ++i)
+        if (!dev_ptrs[i]) return fail(ctx, USRT_ERR_ARG, "set_hit_mirrors: null mirror %d", i);
+    ctx->mirrors = HitMirrors{};
+    for (int i = 0; i < count; ++i) ctx->mirrors.ptr[i] = static_cast<usrt_raycast_result*>(dev_ptrs[i]);
+    ctx->mirrors.count = count;
+    return USRT_OK;
+}
+
 int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
                        const float camera_to_world[16], int y0, int y1, usrt_raycast_result* host_out) {
     NEED_CTX(ctx);
@@ -628,7 +641,7 @@ int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plan
     TraceScene s{ctx->packed_nodes, ctx->packed_tris, ctx->bvh};
     const int rows = y1 - y0;
     if (!host_out || rows <= 0) {
-        CU(ctx, launch_trace_primary(s, p, ctx->hits, ctx->trace_mode, ctx->stream));
+        CU(ctx, launch_trace_primary(s, p, ctx->hits, ctx->trace_mode, ctx->stream, ctx->mirrors));
         ctx->launches += rows > 0 ? 1 : 0;
         return USRT_OK;
     }
@@ -642,7 +655,9 @@ int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plan
         alias = static_cast<usrt_raycast_result*>(attr.devicePointer);
     else
         cudaGetLastError();                               // clear the "not a CUDA pointer" status
-    CU(ctx, launch_trace_primary(s, p, ctx->hits, ctx->trace_mode, ctx->stream, alias));
+    HitMirrors mirrors = ctx->mirrors;
+    if (alias) mirrors.ptr[mirrors.count++] = alias;      // count <= kMaxHitMirrors - 1 by usrt_set_hit_mirrors
+    CU(ctx, launch_trace_primary(s, p, ctx->hits, ctx->trace_mode, ctx->stream, mirrors));
     ctx->launches += 1;
     if (!alias) {
         const size_t off = (size_t)y0 * width;
@@ -674,13 +689,17 @@ int usrt_trace_primary_sharded(usrt_context* ctx, int width, int height, float n
     }
     // rows past the frame (padding of the last block / last shard) are never traced: pre-fill with misses
     CU(ctx, cudaMemsetAsync(out, 0, count * sizeof(usrt_raycast_result), ctx->stream));
+    // (in the mirrors only the last local block can hold such rows: y grows with the local row)
+    const uint64_t last_block = (uint64_t)(local_rows - block_rows) * (uint64_t)width;
+    for (int i = 0; i < ctx->mirrors.count; ++i)
+        CU(ctx, cudaMemsetAsync(ctx->mirrors.ptr[i] + last_block, 0, (count - last_block) * sizeof(usrt_raycast_result), ctx->stream));
     PrimaryParams p;
     p.width = width; p.height = height; p.near_plane = near_plane; p.tan_half_fov = tan_half_fov;
     memcpy(p.m, camera_to_world, sizeof(p.m));
     p.y0 = 0; p.y1 = 0;
     p.block_rows = block_rows; p.shard = shard; p.num_shards = num_shards; p.local_rows = local_rows;
     TraceScene s{ctx->packed_nodes, ctx->packed_tris, ctx->bvh};
-    CU(ctx, launch_trace_primary(s, p, out, ctx->trace_mode, ctx->stream));
+    CU(ctx, launch_trace_primary(s, p, out, ctx->trace_mode, ctx->stream, ctx->mirrors));
     ctx->launches += 1;
     if (host_out) {
         CU(ctx, cudaMemcpyAsync(host_out, out, count * sizeof(usrt_raycast_result), cudaMemcpyDeviceToHost, ctx->stream));

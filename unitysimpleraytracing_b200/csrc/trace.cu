@@ -249,7 +249,7 @@ constexpr int kTileW = 16, kTileH = 8;
 
 template <bool kCulled>
 __global__ void __launch_bounds__(128) k_trace_primary(TraceScene scene, PrimaryParams p, usrt_raycast_result* __restrict__ out,
-                                                       usrt_raycast_result* __restrict__ host_alias) {
+                                                       HitMirrors mirrors) {
     __shared__ uint32_t s_fifo[kCulled ? 1 : kLeafFifo][128];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t x = blockIdx.x * kTileW + (warp & 1u) * 8u + (lane & 7u);
@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(128) k_trace_primary(TraceScene scene, Primary
         if (!valid) return;
     }
     store_hit(out, (size_t)out_row * (size_t)p.width + x, h);          // frame mode: record index = y*W + x
-    if (host_alias != nullptr) store_hit(host_alias, (size_t)out_row * (size_t)p.width + x, h);
+#pragma unroll
+    for (int j = 0; j < kMaxHitMirrors; ++j)                           // pinned host frame / peer GPUs' frame slots
+        if (j < mirrors.count) store_hit(mirrors.ptr[j], (size_t)out_row * (size_t)p.width + x, h);
 }
 
 template <bool kCulled>
@@ -305,12 +307,12 @@ __global__ void __launch_bounds__(128) k_trace_rays(TraceScene scene, const floa
 }  // namespace
 
 cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p, usrt_raycast_result* out, int mode,
-                                 cudaStream_t stream, usrt_raycast_result* host_alias) {
+                                 cudaStream_t stream, const HitMirrors& mirrors) {
     const int rows = p.num_shards > 0 ? p.local_rows : p.y1 - p.y0;
     if (rows <= 0 || p.width <= 0) return cudaSuccess;
     const dim3 grid((p.width + kTileW - 1) / kTileW, (rows + kTileH - 1) / kTileH);
-    if (mode == 1) k_trace_primary<true><<<grid, 128, 0, stream>>>(scene, p, out, host_alias);
-    else k_trace_primary<false><<<grid, 128, 0, stream>>>(scene, p, out, host_alias);
+    if (mode == 1) k_trace_primary<true><<<grid, 128, 0, stream>>>(scene, p, out, mirrors);
+    else k_trace_primary<false><<<grid, 128, 0, stream>>>(scene, p, out, mirrors);
     return cudaGetLastError();
 }
 

@@ -87,9 +87,16 @@ struct PrimaryParams {
     // ((lr / block_rows) * num_shards + shard) * block_rows + lr % block_rows; record index lr*width + x
     int block_rows, shard, num_shards, local_rows;
 };
-// host_alias (optional): device-visible alias of a page-locked HOST frame; records are written to both.
+// Extra destinations of every hit record, written by the trace kernel itself at the same record index as `out`:
+// the device-visible alias of a page-locked HOST frame (zero-copy readback) and/or peer GPUs' frame slots mapped
+// through CUDA IPC (the ray-sharded all-gather done by the kernel's own stores over NVLink).
+constexpr int kMaxHitMirrors = 9;    // 8 frame slots (own + 7 peers) + the pinned host alias
+struct HitMirrors {
+    usrt_raycast_result* ptr[kMaxHitMirrors];
+    int count;
+};
 cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p, usrt_raycast_result* out, int mode,
-                                 cudaStream_t stream, usrt_raycast_result* host_alias = nullptr);
+                                 cudaStream_t stream, const HitMirrors& mirrors);
 cudaError_t launch_trace_rays(const TraceScene& scene, const float4* rays, uint64_t num_rays, usrt_raycast_result* out,
                               int mode, cudaStream_t stream);
 

@@ -54,14 +54,72 @@ def assemble_frame(gathered, width, height, num_shards, block_rows=8):
     return out.reshape((height * width,) + g.shape[3:])
 
 
+class PeerFrameExchange:
+    """The hit-record all-gather done by the trace kernel's own stores (usrt.h: usrt_set_hit_mirrors). Every
+    rank owns `buffers` frames of world x slot_records records, mapped into every other rank through CUDA IPC;
+    select(b) points this rank's trace calls at slot `rank` of frame b on EVERY rank (own copy included), so when
+    all ranks' kernels have finished -- fence() -- every rank holds the whole frame. No data-path collective."""
+
+    def __init__(self, ctx, slot_records, buffers=2, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.group, self.slot, self.buffers = ctx, group, int(slot_records), buffers
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("PeerFrameExchange: at most 8 ranks (one NVSwitch domain)")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.frame_bytes = self.world * self.slot * 16
+        self.own_ptr, handle = ctx.peer_buffer_create(self.frame_bytes * buffers)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy().reshape(self.world, 64)
+        self.peer_ptr = [self.own_ptr if r == self.rank else ctx.peer_buffer_open(allh[r].tobytes())
+                         for r in range(self.world)]
+        self._fence = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def slot_ptr(self, b, on_rank=None):
+        """Address (in this process) of this rank's slot of frame b in the buffer owned by `on_rank`."""
+        base = self.peer_ptr[self.rank if on_rank is None else on_rank]
+        return base + b * self.frame_bytes + self.rank * self.slot * 16
+
+    def select(self, b, include_own=True):
+        self.ctx.set_hit_mirrors([self.slot_ptr(b, r) for r in range(self.world) if include_own or r != self.rank])
+
+    def fence(self):
+        """Enqueue (current torch stream) the point after which every rank's stores have landed everywhere."""
+        import torch.distributed as dist
+        dist.all_reduce(self._fence, group=self.group)
+
+    def frame(self, b):
+        """Frame b of this rank as a float32 torch tensor view [world * slot_records * 4]."""
+        import torch
+        return torch.as_tensor(_DeviceView(self.own_ptr + b * self.frame_bytes, self.world * self.slot * 4, "<f4"),
+                               device=self.device)
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        self.ctx.set_hit_mirrors([])
+        for r, p in enumerate(self.peer_ptr):
+            if r != self.rank and p:
+                self.ctx.peer_buffer_close(p, True)
+        if self.own_ptr:
+            self.ctx.peer_buffer_close(self.own_ptr, False)
+        self.peer_ptr, self.own_ptr = [], 0
+
+
 class RayShardedDrawer:
     """RaytracingMeshDrawer across GPUs: Awake() builds the replica on this rank's GPU, Update() traces
-    this rank's row blocks and all-gathers the records so every rank ends with the whole frame."""
+    this rank's row blocks and every rank ends with the whole frame. exchange="peer" (default): the trace
+    kernel stores each record into every rank's frame over NVLink (PeerFrameExchange); "nccl": trace, then
+    all-gather."""
 
-    def __init__(self, mesh, rank, world, device=None, block_rows=8, group=None):
+    def __init__(self, mesh, rank, world, device=None, block_rows=8, group=None, exchange="peer"):
         from . import host
         self.rank, self.world, self.block_rows, self.group = rank, world, block_rows, group
         self.device = rank if device is None else device
+        self.exchange, self._peer = exchange, None
         self.drawer = host.RaytracingMeshDrawer(mesh, device=self.device)
 
     def Awake(self):
@@ -78,8 +136,21 @@ class RayShardedDrawer:
         import torch.distributed as dist
         dev = torch.device("cuda", self.device)
         per, local_rows = shard_layout(height, self.world, self.block_rows)
-        local = torch.empty(local_rows * width * 4, dtype=torch.float32, device=dev)
         self.ctx.use_torch_stream()
+        if self.world > 1 and self.exchange == "peer":
+            if self._peer is None or self._peer.slot != local_rows * width:
+                if self._peer is not None:
+                    self._peer.close()
+                self._peer = PeerFrameExchange(self.ctx, local_rows * width, buffers=1, group=self.group)
+            px = self._peer
+            dist.barrier(group=self.group)                     # nobody still reads the previous frame
+            px.select(0, include_own=False)
+            self.ctx.trace_primary_sharded(width, height, near, cameraFov, cameraToWorldMatrix, self.block_rows,
+                                           self.rank, self.world, dev_out=px.slot_ptr(0))
+            px.fence()
+            g = px.frame(0).cpu().numpy().view(RaycastResult).reshape(self.world, local_rows * width)
+            return assemble_frame(g, width, height, self.world, self.block_rows)
+        local = torch.empty(local_rows * width * 4, dtype=torch.float32, device=dev)
         self.ctx.trace_primary_sharded(width, height, near, cameraFov, cameraToWorldMatrix, self.block_rows,
                                        self.rank, self.world, dev_out=local.data_ptr())
         self.ctx.sync()
@@ -92,6 +163,9 @@ class RayShardedDrawer:
         return assemble_frame(g, width, height, self.world, self.block_rows)
 
     def OnDestroy(self):
+        if self._peer is not None:
+            self._peer.close()
+            self._peer = None
         self.drawer.OnDestroy()
 
 

@@ -150,6 +150,11 @@ class Context:
     def peer_buffer_close(self, ptr, opened):
         self._check(self._lib.usrt_peer_buffer_close(self._h, ctypes.c_void_p(ptr), 1 if opened else 0))
 
+    def set_hit_mirrors(self, dev_ptrs):
+        """Peer frame slots every traced hit record is also stored to (usrt_set_hit_mirrors); [] clears."""
+        arr = (ctypes.c_void_p * max(len(dev_ptrs), 1))(*[int(p) for p in dev_ptrs])
+        self._check(self._lib.usrt_set_hit_mirrors(self._h, len(dev_ptrs), arr))
+
     def distribute_keys(self):
         self._check(self._lib.usrt_distribute_keys(self._h))
 
