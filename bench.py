@@ -14,7 +14,8 @@ onesweep radix pass, timed live with CUDA events), `rooflines` (every build kern
 
 N > 1: rays are sharded (BASELINE configs[4] shape, north_star (a)): every rank holds a replica of
 the BVH (rebuilt each step, deterministic), traces its own 1080p sample of an N-spp frame, and the
-hit records are all-gathered over NCCL on a side stream, overlapped with the next step's compute.
+trace kernel stores every hit record into every rank's frame over NVLink peer memory (USRT_BENCH_EXCHANGE=nccl:
+an NCCL all-gather instead). Steps alternate over USRT_BENCH_CONTEXTS (default 3) contexts per GPU.
 """
 import argparse
 import json
@@ -194,55 +195,59 @@ def run_ours(args):
     rays = W * H
     m = camera_for_rank(cam, rank)
 
-    ctx = host.Context(n, device=local_rank)
-    # one non-default torch stream carries everything: the library's kernels (usrt_set_stream) and the
-    # torch.cuda.Events that time them (torch events only see the stream they are recorded on)
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    ctx.set_stream(stream.cuda_stream)
-    ctx.upload_triangles(tris)
+    # D independent contexts (own scene buffers and stream) on this GPU, used round-robin: step i+1's rebuild --
+    # a chain of short, latency-bound kernels -- runs beside step i's traversal. Every step still does all of
+    # its work (full rebuild, full 1080p cast) on its own context; D=1 gives the strictly sequential form,
+    # which is also measured below (`sequential`) because the per-stage times add up to that one.
+    D = max(1, int(os.environ.get("USRT_BENCH_CONTEXTS", "3")))
+    ctxs = [host.Context(n, device=local_rank) for _ in range(D)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(D)]
+    torch.cuda.set_stream(streams[0])
+    for c, st in zip(ctxs, streams):
+        assert st.cuda_stream != 0
+        c.set_stream(st.cuda_stream)       # the library's kernels and the torch events that time them share it
+        c.upload_triangles(tris)
+    ctx, stream = ctxs[0], streams[0]      # the single-context legs (stages, trace-only, sort) run on context 0
 
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     # N > 1: every rank must end each step holding all N frames. exchange "peer" (default): the trace kernel
     # stores each hit record into every rank's frame buffer over NVLink peer memory (usrt_set_hit_mirrors),
-    # a one-element all-reduce on a side stream is the "frame complete" fence; "nccl": trace, then all-gather.
+    # a one-element all-reduce is the "frame complete" fence; "nccl": trace, then all-gather.
     exchange = os.environ.get("USRT_BENCH_EXCHANGE", "peer") if world > 1 else None
-    comm_stream = torch.cuda.Stream() if world > 1 else None
-    peer = None
+    peers, gathered = None, None
     if exchange == "peer":
         from unitysimpleraytracing_b200 import dist as udist
-        peer = udist.PeerFrameExchange(ctx, rays, buffers=2)
-    gathered = [torch.empty(world * rays * 4, dtype=torch.float32, device=dev) for _ in range(2)] if exchange == "nccl" else None
-    hit_copy = [torch.empty(rays * 4, dtype=torch.float32, device=dev) for _ in range(2)] if exchange == "nccl" else None
+        peers = [udist.PeerFrameExchange(c, rays, buffers=1) for c in ctxs]
+        for px in peers:
+            px.select(0)
+    elif exchange == "nccl":
+        gathered = [torch.empty(world * rays * 4, dtype=torch.float32, device=dev) for _ in range(D)]
 
-    def step(i, ev0=None, ev1=None):
-        flush.fill_(i & 0xFF)                                           # L2 flush, outside the event pair
-        if ev0 is not None:
-            ev0.record(stream)
-        ctx.rebuild()
-        if peer is not None:
-            stream.wait_stream(comm_stream)        # fence of step i-1 passed: every rank is done with frame buffer i&1
-            peer.select(i & 1)
-        ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=False)
-        if peer is not None:
-            comm_stream.wait_stream(stream)
-            with torch.cuda.stream(comm_stream):
-                peer.fence()
-        elif world > 1:
-            # hand the frame to the comm stream: copy out of the context's hit buffer, then all-gather
-            # there while the next step computes here
-            ptr, cnt = ctx.hits_device()
-            src = _as_tensor(torch, ptr, cnt * 4, dev)
-            buf = i & 1
-            stream.wait_stream(comm_stream)                             # buffer `buf` free again (2 steps ago)
-            hit_copy[buf].copy_(src, non_blocking=True)
-            comm_stream.wait_stream(stream)
-            with torch.cuda.stream(comm_stream):
-                dist.all_gather_into_tensor(gathered[buf], hit_copy[buf])
-        if ev1 is not None:
-            ev1.record(stream)
+    def step(i):
+        j = i % D
+        c = ctxs[j]
+        with torch.cuda.stream(streams[j]):
+            c.rebuild()
+            c.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=False)
+            if peers is not None:
+                peers[j].fence()           # stream j resumes (step i+D) once every rank's frame i has landed everywhere
+            elif world > 1:
+                ptr, cnt = c.hits_device()
+                dist.all_gather_into_tensor(gathered[j], _as_tensor(torch, ptr, cnt * 4, dev))
+
+    def run_steps(k):
+        """k steps; device time from before the first kernel to after the last one, over all D streams."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(ev0)
+        for i in range(k):
+            step(i)
+        for st in streams[1:]:
+            streams[0].wait_stream(st)
+        ev1.record(streams[0])
+        return ev0, ev1
 
     def barrier():
         torch.cuda.synchronize()
@@ -250,47 +255,60 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    run_steps(max(args.warmup, 3, D))
     barrier()
 
     # ---- timed region -------------------------------------------------------------------------
-    launches0 = ctx.kernel_launches
+    launches0 = sum(c.kernel_launches for c in ctxs)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage_acc = {}
     sort_acc = {}
     t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        step(i, *evs[i])
+    ev0, ev1 = run_steps(args.steps)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = ctx.kernel_launches - launches0
+    launches = sum(c.kernel_launches for c in ctxs) - launches0
+    total_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * rays / (ms_per_step * 1e-3) / 1e6
+    if peers is not None:
+        for px in peers:
+            px.close()                     # clears the mirrors: the legs below are single-GPU
+        barrier()
+
+    # ---- the same step strictly sequential on ONE context, L2 flushed between steps, one event pair per step
+    def seq_step(i, e0=None, e1=None):
+        flush.fill_(i & 0xFF)                                           # L2 flush, outside the event pair
+        if e0 is not None:
+            e0.record(stream)
+        ctx.rebuild()
+        ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=False)
+        if e1 is not None:
+            e1.record(stream)
+
+    seq_steps = min(args.steps, 100)
+    seq_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(seq_steps)]
+    for i in range(3):
+        seq_step(i)
+    for i in range(seq_steps):
+        seq_step(i, *seq_ev[i])
+    torch.cuda.synchronize()
+    seq_ms = statistics.mean(a.elapsed_time(b) for a, b in seq_ev)
     # per-stage device times (events recorded inside the library on the same stream), on extra
-    # steps of the same workload so that the queries' host syncs stay out of the timed region
+    # steps of the same workload so that the queries' host syncs stay out of the timed regions
     ctx.enable_stage_timing(True)       # (timed rebuilds are enqueued launch by launch, untimed ones replay a CUDA graph)
     for i in range(5):
-        step(i)
+        seq_step(i)
         for k, v in ctx.last_rebuild_ms().items():
             stage_acc.setdefault(k, []).append(v)
         for k, v in ctx.last_sort_ms().items():
             sort_acc.setdefault(k, []).append(v)
     ctx.enable_stage_timing(False)
     barrier()
-    if peer is not None:
-        peer.close()                       # clears the mirrors: the legs below are single-GPU
-        barrier()
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = sum(step_ms)
-    if world > 1:
-        # the gathers overlap compute; what bounds the job is the slower of the two streams: use the
-        # wall time of the whole region (device-synchronised on both sides) minus nothing
-        total_ms = max(total_ms, t_wall * 1e3 - _flush_ms(torch, flush, stream) * args.steps)
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = world * rays / (ms_per_step * 1e-3) / 1e6
 
     stages = {k: statistics.mean(v) for k, v in stage_acc.items()}
     stages["sort_kernels"] = {k: statistics.mean(v) for k, v in sort_acc.items()}
@@ -310,26 +328,50 @@ def run_ours(args):
     line = None
     if rank == 0:
         # ---- e2e: the same step through the C ABI with HOST buffers -------------------------------
+        # Frames are pipelined over two contexts: frame i+1's upload (copy engine, PCIe) overlaps frame i's
+        # kernels; every frame still pays its own 128 MiB upload and its own 33 MB of hit records, which the
+        # trace kernel writes straight into the page-locked frame. The strictly synchronous form follows.
         pinned_tris = torch.from_numpy(tris.view(np.uint8).reshape(-1)).pin_memory()
-        pinned_hits = torch.empty(rays * 16, dtype=torch.uint8).pin_memory()
         tris_h = pinned_tris.numpy().view(tris.dtype)
-        hits_h = pinned_hits.numpy().view(np.dtype([("distance", "<f4"), ("triangleIndex", "<u4"), ("uv", "<f4", 2)]))
-        e2e_steps = max(3, min(args.steps, 10))
+        hit_dtype = np.dtype([("distance", "<f4"), ("triangleIndex", "<u4"), ("uv", "<f4", 2)])
+        E = ctxs[:2] if D >= 2 else [ctxs[0], host.Context(n, device=local_rank)]
+        pinned_hits = [torch.empty(rays * 16, dtype=torch.uint8).pin_memory() for _ in E]
+        hits_h = [p.numpy().view(hit_dtype) for p in pinned_hits]
+        e2e_steps = max(4, min(args.steps, 20))
 
-        def e2e_step():
-            ctx.upload_triangles(tris_h)                  # H2D of the step's input (synchronous)
-            ctx.rebuild()
-            ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=True, out=hits_h)   # D2H of the result
+        def e2e_run(k):
+            for i in range(k):
+                c = E[i % 2]
+                c.sync()                                  # frame i-2 is complete: hits_h[i % 2] has been handed over
+                c.upload_triangles_async(tris_h)          # H2D of the step's input
+                c.rebuild()
+                c.trace_primary_async(W, H, cam["near"], cam["tan_half_fov"], m, hits_h[i % 2])   # D2H of the result
+            for c in E:
+                c.sync()
 
-        for _ in range(2):
-            e2e_step()
+        e2e_run(4)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
+        e2e_run(e2e_steps)
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-        launches_e2e = 0
+
+        def e2e_sync_step():
+            ctx.upload_triangles(tris_h)                  # synchronous H2D
+            ctx.rebuild()
+            ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=True, out=hits_h[0])
+
+        for _ in range(2):
+            e2e_sync_step()
+        frame_sync = hits_h[0].tobytes()
+        assert hits_h[1].tobytes() == frame_sync, "pipelined and synchronous frames differ"
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_sync_step()
+        torch.cuda.synchronize()
+        e2e_sync_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+        if D < 2:
+            E[1].close()
 
         # ---- sort leg: 2^26 (key, value) pairs resident in HBM ------------------------------------
         ns = 1 << SORT_LOG2
@@ -391,8 +433,14 @@ def run_ours(args):
             "dtype": "f32+u32", "data": "synthetic",
             "config": {"workload": "configs[1]: 1,048,576-tri sphere+height-field, full rebuild + 1920x1080 primary rays",
                        "triangles": int(n), "rays_per_step_per_gpu": rays, "trace_mode": "strict (reference visiting order, no culling)",
-                       "l2": "flushed between timed steps (512 MiB write) and the scene (357 MB) exceeds the 126 MB L2",
+                       "contexts": D,
+                       "l2": ("no flush in the timed region: the %d contexts used round-robin hold 357 MB of scene buffers each, "
+                              "far beyond the 126 MB L2" % D) if D > 1 else
+                             "not flushed; the scene buffers (357 MB) exceed the 126 MB L2 (see `sequential` for the flushed form)",
                        "parallelism": "1 GPU" if world == 1 else "ray-sharded x%d, replicated BVH, %s" % (world, "hit records stored to every rank by the trace kernel over NVLink peer memory" if exchange == "peer" else "all-gather of hit records overlapped")},
+            "sequential": {"ms_per_step": seq_ms, "value": rays / (seq_ms * 1e-3) / 1e6, "steps": seq_steps,
+                           "note": "same step on ONE context, L2 flushed (512 MiB write) between steps, one CUDA event pair per "
+                                   "step on this rank; stages_ms add up to this"},
             "stages_ms": stages,
             "trace_mrays_s": rays / (trace_ms * 1e-3) / 1e6,
             "build_ms": stages["total"],
@@ -409,7 +457,10 @@ def run_ours(args):
                                        "time extrapolated by rows" % (cs["build_s"] * 1e3, rows, H, threads)},
             "e2e": {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(rays * 16),
-                    "note": "usrt_upload_triangles(host) + usrt_rebuild + usrt_trace_primary(host_out), pinned host buffers, 1 GPU"},
+                    "synchronous_ms_per_step": e2e_sync_ms, "synchronous_value": rays / (e2e_sync_ms * 1e-3) / 1e6,
+                    "note": "per frame: usrt_upload_triangles_async(pinned host) + usrt_rebuild + usrt_trace_primary_async(pinned "
+                            "host frame), frames alternate over two contexts so the next upload overlaps the kernels; "
+                            "synchronous_* = one context, every call blocking; 1 GPU"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
@@ -417,7 +468,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if line is not None:
         print(json.dumps(line), flush=True)
 

@@ -83,6 +83,9 @@ uint32_t usrt_triangles_length(const usrt_context* ctx);   /* MeshBufferContaine
 /* Copy n packed triangles to the device (synchronous) and re-initialise keys/indices/nodes as the
  * constructor does (:108-115). Does not compute Morton codes; see usrt_morton. */
 int usrt_upload_triangles(usrt_context* ctx, const usrt_triangle* host_triangles, uint32_t n);
+/* Same, asynchronous: host_triangles must be page-locked and stay untouched until usrt_sync (or a later
+ * synchronising call) returns. With two contexts on one GPU, frame i+1's upload overlaps frame i's kernels. */
+int usrt_upload_triangles_async(usrt_context* ctx, const usrt_triangle* pinned_host_triangles, uint32_t n);
 /* Same, from a DEVICE pointer (async, device-to-device). */
 int usrt_set_triangles_device(usrt_context* ctx, const void* dev_triangles, uint32_t n);
 /* K1 -- the CPU loop of MeshBufferContainer.cs:123-146 as a kernel: padded AABB, centroid of the padded
@@ -154,6 +157,10 @@ int usrt_set_hit_mirrors(usrt_context* ctx, int count, void* const* dev_ptrs);
  * the device copy stays readable through usrt_hits_device. */
 int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
                        const float camera_to_world[16], int y0, int y1, usrt_raycast_result* host_out);
+/* Full frame, asynchronous: pinned_host_out must be page-locked; the kernel writes the records straight into it
+ * and the call returns once enqueued -- read the frame after usrt_sync. */
+int usrt_trace_primary_async(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
+                             const float camera_to_world[16], usrt_raycast_result* pinned_host_out);
 /* Ray sharding across GPUs against a replicated BVH (north_star (a)): shard s of S traces the row
  * blocks b (block = block_rows consecutive rows) with b % S == s -- interleaved for load balance -- in
  * ONE launch and writes them compactly: local row lr = (b / S) * block_rows + row_in_block, record

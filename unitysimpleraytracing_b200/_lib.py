@@ -27,6 +27,7 @@ SIGNATURES = {
     "usrt_capacity": (_c.c_uint32, [_P]),
     "usrt_triangles_length": (_c.c_uint32, [_P]),
     "usrt_upload_triangles": (_c.c_int, [_P, _P, _c.c_uint32]),
+    "usrt_upload_triangles_async": (_c.c_int, [_P, _P, _c.c_uint32]),
     "usrt_set_triangles_device": (_c.c_int, [_P, _P, _c.c_uint32]),
     "usrt_upload_bvh": (_c.c_int, [_P, _c.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
     "usrt_morton": (_c.c_int, [_P]),
@@ -47,6 +48,7 @@ SIGNATURES = {
     "usrt_enable_stage_timing": (_c.c_int, [_P, _c.c_int]),
     "usrt_last_rebuild_ms": (_c.c_int, [_P, _c.POINTER(_c.c_float)]),
     "usrt_last_sort_ms": (_c.c_int, [_P, _c.POINTER(_c.c_float)]),
+    "usrt_trace_primary_async": (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _P, _P]),
     "usrt_trace_primary": (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _P, _c.c_int, _c.c_int, _P]),
     "usrt_trace_primary_sharded": (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _P, _c.c_int, _c.c_int,
                                               _c.c_int, _P, _P]),

@@ -310,6 +310,24 @@ int usrt_upload_triangles(usrt_context* ctx, const usrt_triangle* host_triangles
     return USRT_OK;
 }
 
+int usrt_upload_triangles_async(usrt_context* ctx, const usrt_triangle* pinned_host_triangles, uint32_t n) {
+    NEED_CTX(ctx);
+    if (!pinned_host_triangles || n > ctx->capacity)
+        return fail(ctx, USRT_ERR_ARG, "upload_triangles_async: n=%u capacity=%u", n, ctx->capacity);
+    if (int r = bind_device(ctx)) return r;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, pinned_host_triangles) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        return fail(ctx, USRT_ERR_ARG, "upload_triangles_async: host memory must be page-locked");
+    }
+    if (int r = reset_scene_buffers(ctx, n, ctx->dirty_n)) return r;
+    ctx->dirty_n = n;
+    CU(ctx, cudaMemcpyAsync(ctx->triangles, pinned_host_triangles, (size_t)n * sizeof(usrt_triangle), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n = n;
+    ctx->stage = ST_TRIS;
+    return USRT_OK;
+}
+
 int usrt_set_triangles_device(usrt_context* ctx, const void* dev_triangles, uint32_t n) {
     NEED_CTX(ctx);
     if (!dev_triangles || n > ctx->capacity) return fail(ctx, USRT_ERR_ARG, "set_triangles_device: n=%u capacity=%u", n, ctx->capacity);
@@ -665,6 +683,34 @@ int usrt_trace_primary(usrt_context* ctx, int width, int height, float near_plan
                                 cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return USRT_OK;
+}
+
+int usrt_trace_primary_async(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
+                             const float camera_to_world[16], usrt_raycast_result* pinned_host_out) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_BVH)) return fail(ctx, USRT_ERR_STATE, "trace: BVH not built");
+    if (width <= 0 || height <= 0 || !camera_to_world || !pinned_host_out)
+        return fail(ctx, USRT_ERR_ARG, "trace_primary_async: bad frame %dx%d or null output", width, height);
+    if (int r = bind_device(ctx)) return r;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, pinned_host_out) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+        cudaGetLastError();
+        return fail(ctx, USRT_ERR_ARG, "trace_primary_async: host memory must be page-locked");
+    }
+    const uint64_t count = (uint64_t)width * (uint64_t)height;
+    if (int r = ensure_hits(ctx, count)) return r;
+    ctx->hits_count = count;
+    PrimaryParams p;
+    p.width = width; p.height = height; p.near_plane = near_plane; p.tan_half_fov = tan_half_fov;
+    memcpy(p.m, camera_to_world, sizeof(p.m));
+    p.y0 = 0; p.y1 = height;
+    p.block_rows = 1; p.shard = 0; p.num_shards = 0; p.local_rows = 0;
+    TraceScene s{ctx->packed_nodes, ctx->packed_tris, ctx->bvh};
+    HitMirrors mirrors = ctx->mirrors;
+    mirrors.ptr[mirrors.count++] = static_cast<usrt_raycast_result*>(attr.devicePointer);
+    CU(ctx, launch_trace_primary(s, p, ctx->hits, ctx->trace_mode, ctx->stream, mirrors));
+    ctx->launches += 1;
     return USRT_OK;
 }
 

@@ -99,6 +99,13 @@ class Context:
         tris = np.ascontiguousarray(tris, dtype=Triangle)
         self._check(self._lib.usrt_upload_triangles(self._h, _ptr(tris), len(tris)))
 
+    def upload_triangles_async(self, pinned_tris):
+        """pinned_tris: a Triangle array over page-locked memory (e.g. a view of a torch pin_memory() tensor);
+        it must stay untouched until sync()."""
+        if pinned_tris.dtype != Triangle or not pinned_tris.flags["C_CONTIGUOUS"]:
+            raise ValueError("upload_triangles_async needs a contiguous Triangle array")
+        self._check(self._lib.usrt_upload_triangles_async(self._h, _ptr(pinned_tris), len(pinned_tris)))
+
     def set_triangles_device(self, dev_ptr, n):
         self._check(self._lib.usrt_set_triangles_device(self._h, ctypes.c_void_p(dev_ptr), n))
 
@@ -191,6 +198,13 @@ class Context:
         self._check(self._lib.usrt_trace_primary(self._h, width, height, float(near), float(tan_half_fov), _ptr(m),
                                                  y0, y1, _ptr(out) if download else None))
         return out
+
+    def trace_primary_async(self, width, height, near, tan_half_fov, cam_to_world, pinned_out):
+        """Enqueue a full-frame trace whose records land in `pinned_out` (page-locked RaycastResult array);
+        readable after sync()."""
+        m = np.ascontiguousarray(cam_to_world, np.float32).reshape(16)
+        self._check(self._lib.usrt_trace_primary_async(self._h, width, height, float(near), float(tan_half_fov),
+                                                       _ptr(m), _ptr(pinned_out)))
 
     def trace_primary_sharded(self, width, height, near, tan_half_fov, cam_to_world, block_rows, shard, num_shards,
                               dev_out=None, download=False):
