@@ -117,6 +117,42 @@ def test_pinned_host_frame_is_written_directly_and_matches_staged_copy(usrt):
     ctx.close()
 
 
+def test_async_upload_and_trace_pipeline_over_two_contexts(usrt):
+    """usrt_upload_triangles_async / usrt_trace_primary_async: frames alternating over two contexts (the e2e
+    pipeline of bench.py) give the frames the blocking calls give; pageable memory is refused, not copied."""
+    import torch
+    from unitysimpleraytracing_b200.scene_types import RaycastResult
+    cam = meshes.SCENE_SOUP_CAMERA
+    scenes = [meshes.uniform_soup(20000, seed=s) for s in (1, 2, 3, 4, 5)]
+    w, h = 256, 144
+    want = []
+    with usrt.Context(20000) as c:
+        for t in scenes:
+            c.upload_triangles(t); c.rebuild()
+            want.append(c.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"]).tobytes())
+    pin_t = [torch.from_numpy(t.view(np.uint8).reshape(-1).copy()).pin_memory() for t in scenes]
+    pin_h = [torch.zeros(w * h * 16, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    ctxs = [usrt.Context(20000) for _ in range(2)]
+    got = {}
+    for i, t in enumerate(scenes):
+        c = ctxs[i % 2]
+        c.sync()
+        if i >= 2:
+            got[i - 2] = pin_h[i % 2].numpy().tobytes()
+        c.upload_triangles_async(pin_t[i].numpy().view(scenes[i].dtype)); c.rebuild()
+        c.trace_primary_async(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], pin_h[i % 2].numpy().view(RaycastResult))
+    for i in (len(scenes) - 2, len(scenes) - 1):
+        ctxs[i % 2].sync()
+        got[i] = pin_h[i % 2].numpy().tobytes()
+    assert [got[i] for i in range(len(scenes))] == want
+    with pytest.raises(_lib.UsrtError, match="page-locked"):
+        ctxs[0].upload_triangles_async(scenes[0].copy())
+    with pytest.raises(_lib.UsrtError, match="page-locked"):
+        ctxs[0].trace_primary_async(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], np.zeros(w * h, RaycastResult))
+    for c in ctxs:
+        c.close()
+
+
 def test_hit_mirrors_receive_every_record(usrt):
     """usrt_set_hit_mirrors: the trace kernel stores each record to up to 8 more device frames (peer GPUs' slots
     in the multi-GPU drawer; plain device buffers here), together with the zero-copy pinned host frame."""
