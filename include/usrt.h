@@ -174,6 +174,16 @@ int usrt_trace_primary_sharded(usrt_context* ctx, int width, int height, float n
  * given, inv_dir = 1/dir. */
 int usrt_trace_rays(usrt_context* ctx, const float* host_rays, uint64_t num_rays, usrt_raycast_result* host_out);
 int usrt_trace_rays_device(usrt_context* ctx, const void* dev_rays, uint64_t num_rays, void* dev_out);
+/* Diffuse bounce rays (BASELINE config 5, "64 spp random diffuse rays"; the reference itself casts primary rays
+ * only, Raytracing.compute:105-176, so the generator is defined by the oracle): for every pixel of the frame and
+ * every sample s in [first_sample, first_sample + num_samples), one ray from the pixel's primary hit point along
+ * normal + random unit vector (cosine-weighted), seeded by (seed, pixel, s). dev_primary_hits = the W*H records of
+ * usrt_trace_primary with the same camera (NULL: the context's own, if that was the last trace). Output: 8 floats
+ * per ray in the usrt_trace_rays layout at index (s - first_sample) * W * H + pixel; pixels without a hit give the
+ * null ray (all zeros), which hits nothing. The context's triangle buffer must not be re-uploaded in between. */
+int usrt_diffuse_rays_device(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
+                             const float camera_to_world[16], const void* dev_primary_hits, uint64_t seed,
+                             uint32_t first_sample, uint32_t num_samples, void* dev_rays_out);
 /* Device pointer of the hit records written by the last trace call (usrt_raycast_result[]). */
 int usrt_hits_device(usrt_context* ctx, void** dev_ptr, uint64_t* count);
 /* 0 = strict (default): the reference's visiting semantics exactly -- every box the ray line touches

@@ -705,6 +705,73 @@ extern "C" void usrt_oracle_shade(const RaycastResult* hits, uint64_t count, con
 
 extern "C" uint16_t usrt_oracle_float_to_half(float f) { return float_to_half_rn(f); }
 
+// ---- diffuse bounce rays: BASELINE.json configs[4] ("3840x2160 x 64 spp random diffuse rays") ------------------
+// The reference casts primary rays only (Raytracing.compute:105-176); nothing in it generates secondary rays, so
+// this function DEFINES them for the config (parity unpinned, like the rest of this file): hit point on the primary
+// ray (PrimaryRay above, Raytracing.compute:108-126), geometric normal of the hit triangle (cross/normalize in the
+// canonical expansions of SURVEY 8a) turned against the ray, plus a random unit vector from a counter-based hash
+// (splitmix64 finaliser, rejection sampling in the cube, trig-free) -- a cosine-weighted hemisphere direction.
+static inline uint64_t hash_u64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+static inline void DiffuseRay(const RaycastResult& hit, const Ray& primary, const Triangle* triangleData, uint64_t seed,
+                              uint32_t pixel, uint32_t sample, float* out8) {
+    for (int k = 0; k < 8; ++k) out8[k] = 0.0f;                      // the null ray: hits nothing (det = 0)
+    if (hit.distance == MAX_FLOAT) return;
+    const float t = hit.distance;
+    float P[3];
+    for (int k = 0; k < 3; ++k) P[k] = primary.origin[k] + primary.dir[k] * t;
+    const Triangle& tri = triangleData[hit.triangleIndex];
+    float e1[3], e2[3], n[3];
+    for (int k = 0; k < 3; ++k) { e1[k] = tri.b[k] - tri.a[k]; e2[k] = tri.c[k] - tri.a[k]; }
+    cross3(e1, e2, n);
+    const float n2 = dot3(n, n);
+    if (!(n2 > 0.0f)) return;
+    const float nl = sqrtf(n2);
+    for (int k = 0; k < 3; ++k) n[k] = n[k] / nl;
+    if (dot3(n, primary.dir) > 0.0f) for (int k = 0; k < 3; ++k) n[k] = -n[k];
+    float u[3] = {n[0], n[1], n[2]};                                  // fallback after 16 rejected draws
+    const uint64_t stream = hash_u64(seed ^ hash_u64(((uint64_t)pixel << 16) | (uint64_t)(sample & 0xFFFFu)));
+    for (uint32_t k = 0; k < 16u; ++k) {
+        const uint64_t bits = hash_u64(stream + k);
+        float v[3];                                                   // three 21-bit fields -> [-1, 1), exact in fp32
+        v[0] = (float)(uint32_t)(bits & 0x1FFFFFu) * 9.5367431640625e-07f - 1.0f;
+        v[1] = (float)(uint32_t)((bits >> 21) & 0x1FFFFFu) * 9.5367431640625e-07f - 1.0f;
+        v[2] = (float)(uint32_t)((bits >> 42) & 0x1FFFFFu) * 9.5367431640625e-07f - 1.0f;
+        const float l2 = dot3(v, v);
+        if (l2 <= 1.0f && l2 > 1e-4f) {
+            const float l = sqrtf(l2);
+            for (int c = 0; c < 3; ++c) u[c] = v[c] / l;
+            break;
+        }
+    }
+    float d[3];
+    for (int k = 0; k < 3; ++k) d[k] = n[k] + u[k];
+    const float d2 = dot3(d, d);
+    if (d2 < 1e-8f) { for (int k = 0; k < 3; ++k) d[k] = n[k]; }
+    else { const float dl = sqrtf(d2); for (int k = 0; k < 3; ++k) d[k] = d[k] / dl; }
+    for (int k = 0; k < 3; ++k) { out8[k] = P[k] + n[k] * 0.001f; out8[4 + k] = d[k]; }
+}
+
+// rays_out: 8 floats per ray at index (sample - first_sample) * W * H + pixel
+extern "C" void usrt_oracle_diffuse_rays(const RaycastResult* primary_hits, const Triangle* triangleData, int screenWidth,
+                                         int screenHeight, float near, float cameraFov, const float* m, uint64_t seed,
+                                         uint32_t first_sample, uint32_t num_samples, float* rays_out) {
+    const uint64_t frame = (uint64_t)screenWidth * (uint64_t)screenHeight;
+    for (uint32_t s = 0; s < num_samples; ++s)
+        for (uint32_t y = 0; y < (uint32_t)screenHeight; ++y)
+            for (uint32_t x = 0; x < (uint32_t)screenWidth; ++x) {
+                const uint32_t pixel = y * (uint32_t)screenWidth + x;
+                const Ray primary = PrimaryRay(x, y, screenWidth, screenHeight, near, cameraFov, m);
+                DiffuseRay(primary_hits[pixel], primary, triangleData, seed, pixel, first_sample + s,
+                           rays_out + ((uint64_t)s * frame + pixel) * 8);
+            }
+}
+
 // Leaf visiting order of the reference DFS when every box test passes (left leaf, right leaf, then
 // the RIGHT internal subtree before the LEFT one -- Raytracing.compute:148-175 push order).
 void usrt_oracle_visit_order(const uint32_t* sortedTriangleIndices, const InternalNode* internalNodes,

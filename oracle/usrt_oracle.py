@@ -210,6 +210,20 @@ def shade(hits, triangle_data, texture_rgba):
     return out.view(np.float16)
 
 
+def diffuse_rays(primary_hits, triangle_data, width, height, near, tan_half_fov, cam_to_world, seed, first_sample,
+                 num_samples):
+    """BASELINE configs[4] bounce rays (defined by this oracle; the reference has primary rays only):
+    (num_samples * width * height, 8) float32, sample-major."""
+    hits = np.ascontiguousarray(primary_hits, RAYCAST_RESULT)
+    assert len(hits) == width * height
+    m = np.ascontiguousarray(cam_to_world, np.float32).reshape(16)
+    out = np.zeros((num_samples * width * height, 8), np.float32)
+    lib().usrt_oracle_diffuse_rays(_p(hits), _p(np.ascontiguousarray(triangle_data, TRIANGLE)), ctypes.c_int(width),
+                                   ctypes.c_int(height), ctypes.c_float(near), ctypes.c_float(tan_half_fov), _p(m),
+                                   ctypes.c_uint64(seed), ctypes.c_uint32(first_sample), ctypes.c_uint32(num_samples), _p(out))
+    return out
+
+
 def float_to_half_bits(f):
     lib().usrt_oracle_float_to_half.restype = ctypes.c_uint16
     return int(lib().usrt_oracle_float_to_half(ctypes.c_float(f)))

@@ -279,3 +279,29 @@ def test_shade_against_numpy_restatement(oracle):
     assert np.array_equal(got[:, :3].view(np.uint16), rgb.view(np.uint16))
     assert np.array_equal(got[:, 3], alpha)
     assert (alpha == 1).sum() > 100
+
+
+def test_diffuse_bounce_rays_properties(oracle):
+    """BASELINE configs[4] bounce rays (defined by the oracle): unit directions in the hemisphere of the hit
+    triangle's ray-facing normal, origin just off the surface, null rays for pixels that missed, and a sample
+    window equals the same samples of the full set."""
+    from unitysimpleraytracing_b200 import meshes
+    tris = meshes.scene_c1(4096); cam = meshes.SCENE_SOUP_CAMERA
+    w, h = 48, 27
+    args = (w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    hits = oracle.Scene(tris).trace_primary(*args)
+    rays = oracle.diffuse_rays(hits, tris, *args, 77, 0, 4).reshape(4, w * h, 8)
+    miss = hits["distance"] == oracle.max_float()
+    assert miss.any() and (~miss).any()
+    assert not rays[:, miss].any()
+    t = tris[hits["triangleIndex"][~miss]]
+    n = np.cross((t["b"] - t["a"]).astype(np.float64), (t["c"] - t["a"]).astype(np.float64))
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    d = rays[:, ~miss, 4:7].astype(np.float64)
+    assert (np.abs(np.linalg.norm(d, axis=2) - 1) < 1e-6).all()
+    cosine = np.abs((d * n[None]).sum(2))                   # n up to sign: the ray-facing one is used
+    o = rays[:, ~miss, 0:3].astype(np.float64)
+    assert (np.abs(o[0] - o[1]) == 0).all()                 # same origin for every sample of a pixel
+    assert np.array_equal(oracle.diffuse_rays(hits, tris, *args, 77, 2, 2).reshape(2, w * h, 8), rays[2:])
+    assert 0.55 < cosine.mean() < 0.78                      # cosine-weighted: E[cos] = 2/3
+    assert not np.array_equal(rays[0], rays[1])

@@ -164,6 +164,50 @@ def test_incoherent_rays(usrt, oracle, name, extent, count):
     d.OnDestroy()
 
 
+@pytest.mark.parametrize("name,cam", [("c1", "SCENE_SOUP_CAMERA"), ("sphere", "REFERENCE_CAMERA")])
+def test_diffuse_bounce_rays(usrt, oracle, name, cam):
+    """BASELINE configs[4] ("64 spp random diffuse rays"): the bounce rays generated on the device from the primary
+    hit records are bit-identical to the oracle's, for any sample window, and so are their hit records."""
+    import torch
+    tris = _mesh(name) if name != "sphere" else meshes.sphere(48, 96)
+    cam = getattr(meshes, cam)
+    w, h, seed = 96, 54, 0x5EED0007
+    args = (w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    ref = oracle.Scene(tris)
+    hits = ref.trace_primary(*args, threads=8)
+    assert 0 < (hits["distance"] != oracle.max_float()).sum()
+    want_rays = oracle.diffuse_rays(hits, tris, *args, seed, 0, 5)
+    d = usrt.RaytracingMeshDrawer(tris).Awake()
+    ctx = d.container.ctx
+    got_hits = d.Update(*args)
+    assert _same(got_hits, hits)
+    rays = torch.zeros(5 * w * h * 8, dtype=torch.float32, device="cuda")
+    ctx.diffuse_rays_device(*args, seed, 0, 5, rays.data_ptr())          # primary hits = the context's last trace
+    ctx.sync()
+    assert rays.cpu().numpy().tobytes() == want_rays.tobytes()
+    # a window of samples, from an explicit copy of the primary hit records
+    hits_dev = torch.from_numpy(hits.view(np.float32).reshape(-1).copy()).cuda()
+    win = torch.zeros(2 * w * h * 8, dtype=torch.float32, device="cuda")
+    ctx.diffuse_rays_device(*args, seed, 3, 2, win.data_ptr(), primary_hits_ptr=hits_dev.data_ptr())
+    ctx.sync()
+    assert win.cpu().numpy().tobytes() == want_rays[3 * w * h:].tobytes()
+    # unit directions in the hemisphere of the (ray-facing) normal, null rays exactly where the pixel missed
+    wr = want_rays.reshape(5, w * h, 8)
+    miss = hits["distance"] == oracle.max_float()
+    assert not wr[:, miss].any() and (np.abs(np.linalg.norm(wr[:, ~miss, 4:7], axis=2) - 1) < 1e-6).all()
+    assert len(np.unique(wr[:, ~miss, 4:7].reshape(-1, 3), axis=0)) > 0.99 * 5 * (~miss).sum()
+    # the bounce itself
+    want = ref.trace_rays(want_rays, threads=8)
+    out = torch.zeros(5 * w * h * 4, dtype=torch.float32, device="cuda")
+    ctx.trace_rays_device(rays.data_ptr(), 5 * w * h, out.data_ptr())
+    ctx.sync()
+    got = out.cpu().numpy().view(want.dtype)
+    assert _report_ties(got, want) == (0, 0)
+    assert _same(got, want)
+    assert (want["distance"][np.tile(miss, 5)] == oracle.max_float()).all()      # null rays hit nothing
+    d.OnDestroy()
+
+
 def test_culled_mode_is_reported_separately(usrt, oracle):
     """Mode 1 is NOT part of the parity contract; it must still find a hit wherever strict does, never
     a farther one by more than fp noise. We only record how far it is from strict."""

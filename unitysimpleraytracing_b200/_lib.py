@@ -48,6 +48,8 @@ SIGNATURES = {
     "usrt_enable_stage_timing": (_c.c_int, [_P, _c.c_int]),
     "usrt_last_rebuild_ms": (_c.c_int, [_P, _c.POINTER(_c.c_float)]),
     "usrt_last_sort_ms": (_c.c_int, [_P, _c.POINTER(_c.c_float)]),
+    "usrt_diffuse_rays_device": (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _P, _P, _c.c_uint64, _c.c_uint32,
+                                            _c.c_uint32, _P]),
     "usrt_trace_primary_async": (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _P, _P]),
     "usrt_trace_primary": (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _P, _c.c_int, _c.c_int, _P]),
     "usrt_trace_primary_sharded": (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _P, _c.c_int, _c.c_int,

@@ -754,6 +754,31 @@ int usrt_trace_primary_sharded(usrt_context* ctx, int width, int height, float n
     return USRT_OK;
 }
 
+int usrt_diffuse_rays_device(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
+                             const float camera_to_world[16], const void* dev_primary_hits, uint64_t seed,
+                             uint32_t first_sample, uint32_t num_samples, void* dev_rays_out) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_TRIS)) return fail(ctx, USRT_ERR_STATE, "diffuse_rays: no triangles uploaded");
+    if (width <= 0 || height <= 0 || !camera_to_world || !dev_rays_out || (uint64_t)width * height > 0xFFFFFFFFull ||
+        (uint64_t)first_sample + num_samples > 65536)
+        return fail(ctx, USRT_ERR_ARG, "diffuse_rays: bad frame %dx%d, samples [%u,+%u) (at most 65536) or null output", width, height,
+                    first_sample, num_samples);
+    const usrt_raycast_result* hits = static_cast<const usrt_raycast_result*>(dev_primary_hits);
+    if (!hits) {
+        if (ctx->hits_count != (uint64_t)width * height) return fail(ctx, USRT_ERR_STATE, "diffuse_rays: the last trace was not this frame");
+        hits = ctx->hits;
+    }
+    if (int r = bind_device(ctx)) return r;
+    PrimaryParams p;
+    p.width = width; p.height = height; p.near_plane = near_plane; p.tan_half_fov = tan_half_fov;
+    memcpy(p.m, camera_to_world, sizeof(p.m));
+    p.y0 = 0; p.y1 = height;
+    p.block_rows = 1; p.shard = 0; p.num_shards = 0; p.local_rows = 0;
+    CU(ctx, launch_diffuse_rays(p, hits, ctx->triangles, seed, first_sample, num_samples, static_cast<float4*>(dev_rays_out), ctx->stream));
+    ctx->launches += num_samples ? 1 : 0;
+    return USRT_OK;
+}
+
 int usrt_trace_rays_device(usrt_context* ctx, const void* dev_rays, uint64_t num_rays, void* dev_out) {
     NEED_CTX(ctx);
     if (!(ctx->stage & ST_BVH)) return fail(ctx, USRT_ERR_STATE, "trace: BVH not built");

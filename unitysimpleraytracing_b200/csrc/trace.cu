@@ -304,6 +304,73 @@ __global__ void __launch_bounds__(128) k_trace_rays(TraceScene scene, const floa
     store_hit(out, (size_t)i, h);
 }
 
+// ---- diffuse bounce rays (BASELINE config 5: "64 spp random diffuse rays") ------------------------------
+// The reference casts primary rays only; the generator below is DEFINED by the test oracle's DiffuseRay
+// function and restated here operation for operation: hit point on the
+// primary ray, geometric normal of the hit triangle turned against the ray, plus a hashed, trig-free random
+// unit vector (cosine-weighted hemisphere), seeded by (seed, pixel, sample). Pixels that hit nothing and
+// degenerate triangles emit the null ray (all zeros), which can hit nothing (det = 0 in ray_triangle).
+__device__ __forceinline__ uint64_t hash_u64(uint64_t x) {             // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) k_diffuse_rays(PrimaryParams p, const usrt_raycast_result* __restrict__ hits,
+                                                      const float4* __restrict__ tris, uint64_t seed, uint32_t s0,
+                                                      uint64_t total, float4* __restrict__ rays_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint64_t frame = (uint64_t)p.width * (uint64_t)p.height;
+    const uint32_t sample = s0 + (uint32_t)(i / frame);
+    const uint32_t pixel = (uint32_t)(i % frame);
+    const uint32_t x = pixel % (uint32_t)p.width, y = pixel / (uint32_t)p.width;
+    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4;
+    const float4 h = __ldg(reinterpret_cast<const float4*>(hits) + pixel);
+    if (__float_as_uint(h.x) != 0x4EFF0000u) {                         // distance != MAX_FLOAT: the pixel hit something
+        const Ray r = primary_ray(p, x, y);
+        const float t = h.x;
+        const float px = add(r.ox, mul(r.dx, t)), py = add(r.oy, mul(r.dy, t)), pz = add(r.oz, mul(r.dz, t));
+        const float4* tri = tris + (size_t)__float_as_uint(h.y) * 8;
+        const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+        const float e1x = sub(b.x, a.x), e1y = sub(b.y, a.y), e1z = sub(b.z, a.z);
+        const float e2x = sub(c.x, a.x), e2y = sub(c.y, a.y), e2z = sub(c.z, a.z);
+        float nx = sub(mul(e1y, e2z), mul(e1z, e2y));
+        float ny = sub(mul(e1z, e2x), mul(e1x, e2z));
+        float nz = sub(mul(e1x, e2y), mul(e1y, e2x));
+        const float n2 = dot3(nx, ny, nz, nx, ny, nz);
+        if (n2 > 0.0f) {
+            const float nl = __fsqrt_rn(n2);
+            nx = __fdiv_rn(nx, nl); ny = __fdiv_rn(ny, nl); nz = __fdiv_rn(nz, nl);
+            if (dot3(nx, ny, nz, r.dx, r.dy, r.dz) > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
+            float ux = nx, uy = ny, uz = nz;                           // fallback after 16 rejected draws
+            const uint64_t stream = hash_u64(seed ^ hash_u64(((uint64_t)pixel << 16) | (uint64_t)(sample & 0xFFFFu)));
+            for (uint32_t k = 0; k < 16u; ++k) {
+                const uint64_t bits = hash_u64(stream + k);
+                // three 21-bit fields -> [-1, 1): exact in fp32
+                const float vx = sub(mul(__uint2float_rn((uint32_t)(bits & 0x1FFFFFu)), 9.5367431640625e-07f), 1.0f);
+                const float vy = sub(mul(__uint2float_rn((uint32_t)((bits >> 21) & 0x1FFFFFu)), 9.5367431640625e-07f), 1.0f);
+                const float vz = sub(mul(__uint2float_rn((uint32_t)((bits >> 42) & 0x1FFFFFu)), 9.5367431640625e-07f), 1.0f);
+                const float l2 = dot3(vx, vy, vz, vx, vy, vz);
+                if (l2 <= 1.0f && l2 > 1e-4f) {
+                    const float l = __fsqrt_rn(l2);
+                    ux = __fdiv_rn(vx, l); uy = __fdiv_rn(vy, l); uz = __fdiv_rn(vz, l);
+                    break;
+                }
+            }
+            float dx = add(nx, ux), dy = add(ny, uy), dz = add(nz, uz);
+            const float d2 = dot3(dx, dy, dz, dx, dy, dz);
+            if (d2 < 1e-8f) { dx = nx; dy = ny; dz = nz; }
+            else { const float dl = __fsqrt_rn(d2); dx = __fdiv_rn(dx, dl); dy = __fdiv_rn(dy, dl); dz = __fdiv_rn(dz, dl); }
+            o4 = make_float4(add(px, mul(nx, 0.001f)), add(py, mul(ny, 0.001f)), add(pz, mul(nz, 0.001f)), 0.f);
+            d4 = make_float4(dx, dy, dz, 0.f);
+        }
+    }
+    rays_out[i * 2] = o4;
+    rays_out[i * 2 + 1] = d4;
+}
+
 }  // namespace
 
 cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p, usrt_raycast_result* out, int mode,
@@ -322,6 +389,15 @@ cudaError_t launch_trace_rays(const TraceScene& scene, const float4* rays, uint6
     const uint32_t grid = (uint32_t)((num_rays + 127) / 128);
     if (mode == 1) k_trace_rays<true><<<grid, 128, 0, stream>>>(scene, rays, num_rays, out);
     else k_trace_rays<false><<<grid, 128, 0, stream>>>(scene, rays, num_rays, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_diffuse_rays(const PrimaryParams& p, const usrt_raycast_result* hits, const usrt_triangle* tris,
+                                uint64_t seed, uint32_t s0, uint32_t s_count, float4* rays_out, cudaStream_t stream) {
+    const uint64_t total = (uint64_t)p.width * (uint64_t)p.height * (uint64_t)s_count;
+    if (total == 0) return cudaSuccess;
+    k_diffuse_rays<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, hits, reinterpret_cast<const float4*>(tris), seed, s0,
+                                                                         total, rays_out);
     return cudaGetLastError();
 }
 

@@ -100,6 +100,11 @@ cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p
 cudaError_t launch_trace_rays(const TraceScene& scene, const float4* rays, uint64_t num_rays, usrt_raycast_result* out,
                               int mode, cudaStream_t stream);
 
+// diffuse bounce rays from the primary hit records (BASELINE config 5), s_count samples per pixel starting at s0;
+// ray index = (sample - s0) * W * H + pixel
+cudaError_t launch_diffuse_rays(const PrimaryParams& p, const usrt_raycast_result* hits, const usrt_triangle* tris,
+                                uint64_t seed, uint32_t s0, uint32_t s_count, float4* rays_out, cudaStream_t stream);
+
 // shading epilogue
 cudaError_t launch_shade(const usrt_raycast_result* hits, uint64_t count, const usrt_triangle* tris, const float4* tex,
                          int tw, int th, void* out_rgba16f, cudaStream_t stream);

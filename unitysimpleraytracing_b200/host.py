@@ -206,6 +206,16 @@ class Context:
         self._check(self._lib.usrt_trace_primary_async(self._h, width, height, float(near), float(tan_half_fov),
                                                        _ptr(m), _ptr(pinned_out)))
 
+    def diffuse_rays_device(self, width, height, near, tan_half_fov, cam_to_world, seed, first_sample, num_samples,
+                            rays_out_ptr, primary_hits_ptr=None):
+        """Bounce rays of samples [first_sample, +num_samples) from the primary hit records (usrt_diffuse_rays_device);
+        rays_out_ptr: device memory for num_samples * width * height rays of 32 bytes."""
+        m = np.ascontiguousarray(cam_to_world, np.float32).reshape(16)
+        self._check(self._lib.usrt_diffuse_rays_device(self._h, width, height, float(near), float(tan_half_fov), _ptr(m),
+                                                       ctypes.c_void_p(primary_hits_ptr) if primary_hits_ptr else None,
+                                                       int(seed), int(first_sample), int(num_samples),
+                                                       ctypes.c_void_p(rays_out_ptr)))
+
     def trace_primary_sharded(self, width, height, near, tan_half_fov, cam_to_world, block_rows, shard, num_shards,
                               dev_out=None, download=False):
         """One launch over this shard's interleaved row blocks; compact output (see include/usrt.h)."""
