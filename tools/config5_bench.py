@@ -43,7 +43,8 @@ if a.diffuse:
     prim = torch.empty(frame * 4, dtype=torch.float32, device=dev)
     rays = torch.empty(frame * 8, dtype=torch.float32, device=dev)
     out = torch.empty(spp_rank * frame * 4, dtype=torch.float32, device=dev)
-    gathered = torch.empty(world * out.numel(), dtype=torch.float32, device=dev) if world > 1 else None
+    gathered = torch.empty(world * out.numel(), dtype=torch.float32, device=dev) if world > 1 else None   # [sample][rank][pixel]
+    side = torch.cuda.Stream() if world > 1 else None
 
     def run():
         ctx.trace_primary(*cargs, download=False)       # every rank: the primary frame against its BVH replica
@@ -53,8 +54,13 @@ if a.diffuse:
         for s_ in range(spp_rank):                      # one sample pass = one frame of bounce rays
             ctx.diffuse_rays_device(*cargs, 0x5EED0008, rank * spp_rank + s_, 1, rays.data_ptr(), primary_hits_ptr=prim.data_ptr())
             ctx.trace_rays_device(rays.data_ptr(), frame, out.data_ptr() + s_ * frame * 16)
+            if world > 1:                               # the output gather (16 B per ray), pass by pass beside the next pass
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    dist.all_gather_into_tensor(gathered[s_ * world * frame * 4:(s_ + 1) * world * frame * 4],
+                                                out[s_ * frame * 4:(s_ + 1) * frame * 4])
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)  # the output gather: 16 B per ray
+            torch.cuda.current_stream().wait_stream(side)
 
     spp_save, spp_rank = spp_rank, 1
     run(); torch.cuda.synchronize(); spp_rank = spp_save
