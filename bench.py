@@ -218,10 +218,23 @@ def run_ours(args):
     peers, gathered = None, None
     if exchange == "peer":
         from unitysimpleraytracing_b200 import dist as udist
-        peers = [udist.PeerFrameExchange(c, rays, buffers=1) for c in ctxs]
-        for px in peers:
-            px.select(0)
-    elif exchange == "nccl":
+        # CUDA IPC needs peer access between the GPUs and a shared PID/IPC namespace; if any rank cannot map its
+        # peers, every rank switches to the NCCL all-gather (still this repo's kernels; only the exchange differs)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            peers = [udist.PeerFrameExchange(c, rays, buffers=1) for c in ctxs]
+        except Exception as e:                                          # noqa: BLE001
+            sys.stderr.write("bench.py: peer-memory frame exchange unavailable on rank %d (%s)\n" % (rank, e))
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            for c in ctxs:
+                c.set_hit_mirrors([])
+            peers, exchange = None, "nccl"
+        else:
+            for px in peers:
+                px.select(0)
+    if exchange == "nccl":
         gathered = [torch.empty(world * rays * 4, dtype=torch.float32, device=dev) for _ in range(D)]
 
     def step(i):

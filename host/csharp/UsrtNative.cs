@@ -44,6 +44,14 @@ namespace Usrt
         [DllImport(Lib)] public static extern int usrt_rebuild(IntPtr ctx);
         [DllImport(Lib)] public static extern int usrt_trace_primary(IntPtr ctx, int width, int height, float near, float tanHalfFov,
                                                                     [In] float[] cameraToWorldRowMajor, int y0, int y1, [Out] RaycastResult[] hostOut);
+        // frame pipeline over two contexts: page-locked buffers (e.g. cudaHostAlloc'ed, or Marshal-pinned + cudaHostRegister)
+        [DllImport(Lib)] public static extern int usrt_upload_triangles_async(IntPtr ctx, IntPtr pinnedTriangles, uint n);
+        [DllImport(Lib)] public static extern int usrt_trace_primary_async(IntPtr ctx, int width, int height, float near, float tanHalfFov,
+                                                                          [In] float[] cameraToWorldRowMajor, IntPtr pinnedHostOut);
+        [DllImport(Lib)] public static extern int usrt_diffuse_rays_device(IntPtr ctx, int width, int height, float near, float tanHalfFov,
+                                                                          [In] float[] cameraToWorldRowMajor, IntPtr devPrimaryHits, ulong seed,
+                                                                          uint firstSample, uint numSamples, IntPtr devRaysOut);
+        [DllImport(Lib)] public static extern int usrt_trace_rays_device(IntPtr ctx, IntPtr devRays, ulong numRays, IntPtr devOut);
         [DllImport(Lib)] public static extern int usrt_trace_rays(IntPtr ctx, [In] float[] rays, ulong numRays, [Out] RaycastResult[] hostOut);
         [DllImport(Lib)] public static extern int usrt_upload_texture(IntPtr ctx, [In] float[] rgba, int width, int height);
         [DllImport(Lib)] public static extern int usrt_shade(IntPtr ctx, IntPtr devOut, [Out] ushort[] hostOutRgba16f);

@@ -54,6 +54,53 @@ def assemble_frame(gathered, width, height, num_shards, block_rows=8):
     return out.reshape((height * width,) + g.shape[3:])
 
 
+def map_peer_buffers(ctx, nbytes, group=None):
+    """Allocate `nbytes` on this rank's GPU and map every other rank's buffer of the same call into this process
+    (CUDA IPC over torch.distributed). Returns (own_ptr, [ptr of rank 0's buffer, ...]) with own_ptr at index
+    rank. Collective, and collectively consistent: if any rank cannot allocate or map (no peer access, separate
+    IPC namespaces), every rank releases what it holds and raises RuntimeError -- no rank is left in a collective."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    device = torch.device("cuda", torch.cuda.current_device())
+
+    def everyone(ok):
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return bool(flag.item())
+
+    own_ptr, handle, err = 0, bytes(64), None
+    try:
+        own_ptr, handle = ctx.peer_buffer_create(nbytes)
+    except Exception as e:                                             # noqa: BLE001
+        err = e
+    if not everyone(err is None):
+        if own_ptr:
+            ctx.peer_buffer_close(own_ptr, False)
+        raise RuntimeError("map_peer_buffers: allocation failed on some rank (this rank: %s)" % err)
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+    allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(allh, mine, group=group)
+    allh = allh.cpu().numpy().reshape(world, 64)
+    peer_ptr = [0] * world
+    peer_ptr[rank] = own_ptr
+    try:
+        for r in range(world):
+            if r != rank:
+                peer_ptr[r] = ctx.peer_buffer_open(allh[r].tobytes())
+    except Exception as e:                                             # noqa: BLE001
+        err = e
+    if not everyone(err is None):
+        for r in range(world):
+            if r != rank and peer_ptr[r]:
+                ctx.peer_buffer_close(peer_ptr[r], True)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)                                      # nobody frees a buffer a peer still maps
+        ctx.peer_buffer_close(own_ptr, False)
+        raise RuntimeError("map_peer_buffers: CUDA IPC mapping failed on some rank (this rank: %s)" % err)
+    return own_ptr, peer_ptr
+
+
 class PeerFrameExchange:
     """The hit-record all-gather done by the trace kernel's own stores (usrt.h: usrt_set_hit_mirrors). Every
     rank owns `buffers` frames of world x slot_records records, mapped into every other rank through CUDA IPC;
@@ -69,13 +116,7 @@ class PeerFrameExchange:
             raise ValueError("PeerFrameExchange: at most 8 ranks (one NVSwitch domain)")
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.frame_bytes = self.world * self.slot * 16
-        self.own_ptr, handle = ctx.peer_buffer_create(self.frame_bytes * buffers)
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
-        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
-        dist.all_gather_into_tensor(allh, mine, group=group)
-        allh = allh.cpu().numpy().reshape(self.world, 64)
-        self.peer_ptr = [self.own_ptr if r == self.rank else ctx.peer_buffer_open(allh[r].tobytes())
-                         for r in range(self.world)]
+        self.own_ptr, self.peer_ptr = map_peer_buffers(ctx, self.frame_bytes * buffers, group)
         self._fence = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     def slot_ptr(self, b, on_rank=None):
@@ -105,6 +146,8 @@ class PeerFrameExchange:
             if r != self.rank and p:
                 self.ctx.peer_buffer_close(p, True)
         if self.own_ptr:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)             # collective: every peer has unmapped this rank's buffer
             self.ctx.peer_buffer_close(self.own_ptr, False)
         self.peer_ptr, self.own_ptr = [], 0
 
@@ -285,13 +328,7 @@ class PeerSortExchange:
         self.ctx, self.group, self.capacity = ctx, group, int(capacity)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.own_ptr, handle = ctx.peer_buffer_create(self.capacity * 8)       # keys | values
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
-        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
-        dist.all_gather_into_tensor(allh, mine, group=group)
-        allh = allh.cpu().numpy().reshape(self.world, 64)
-        self.peer_ptr = [self.own_ptr if r == self.rank else ctx.peer_buffer_open(allh[r].tobytes())
-                         for r in range(self.world)]
+        self.own_ptr, self.peer_ptr = map_peer_buffers(ctx, self.capacity * 8, group)       # keys | values
         self._fence = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._hist = torch.zeros(256, dtype=torch.int32, device=self.device)
         self._all_hist = torch.empty(self.world * 256, dtype=torch.int32, device=self.device)
@@ -339,5 +376,7 @@ class PeerSortExchange:
             if r != self.rank and p:
                 self.ctx.peer_buffer_close(p, True)
         if self.own_ptr:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)             # collective: every peer has unmapped this rank's buffer
             self.ctx.peer_buffer_close(self.own_ptr, False)
         self.peer_ptr, self.own_ptr = [], 0
