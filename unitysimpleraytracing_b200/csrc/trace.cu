@@ -162,21 +162,29 @@ __device__ __forceinline__ usrt_raycast_result traverse_strict(const TraceScene&
     best.distance = max_float();                       // Raytracing.compute:129-131
     best.triangleIndex = 0;
     best.uv[0] = 0.0f; best.uv[1] = 0.0f;
-    const uint32_t tid = threadIdx.x;
+    // slot k of this lane = fifo[k][tid]; addressed as a 32-bit shared-window offset so that a push is
+    // {and, shift-add, st.shared} under a predicate instead of a generic-pointer rebuild behind a branch
+    const uint32_t fifo_sh = (uint32_t)__cvta_generic_to_shared(&fifo[0][threadIdx.x]);
+    constexpr uint32_t kSlotBytes = 128u * 4u;
+    constexpr uint32_t kDone = 0xFFFFFFFFu;             // no node left for this lane
 
-    bool alive = valid;
-    if (alive) {                                        // node 0 is popped and its own box tested first (:135-146)
+    uint32_t index = 0;
+    if (valid) {                                        // node 0 is popped and its own box tested first (:135-146)
         const float4 rmin = __ldg(reinterpret_cast<const float4*>(s.bvh));
         const float4 rmax = __ldg(reinterpret_cast<const float4*>(s.bvh) + 1);
         float entry;
-        alive = ray_box(rmin.x, rmin.y, rmin.z, rmax.x, rmax.y, rmax.z, ray, &entry);
+        if (!ray_box(rmin.x, rmin.y, rmin.z, rmax.x, rmax.y, rmax.z, ray, &entry)) index = kDone;
+    } else {
+        index = kDone;
     }
+    uint32_t walking = __popc(__ballot_sync(0xFFFFFFFFu, index != kDone));   // warp-uniform: lanes with nodes left
+    if (walking == 0) return best;                      // off-frame warp, or every ray misses the root box
     uint32_t stack[64];                                // :133 (deferred left siblings only, <= 33 deep)
     int sp = 0;
-    uint32_t index = 0;
-    uint32_t head = 0, count = 0;                       // FIFO state of this lane
+    uint32_t head = 0, tail = 0;                        // FIFO of this lane: running counters, slot = counter & 7
     while (true) {
-        if (alive) {
+        bool finished = false;
+        if (index != kDone) {
             const float4* pn = s.packed_nodes + (size_t)index * 4;
             const Node8 n01 = ldg256(pn), n23 = ldg256(pn + 2);
             const float4 q0 = n01.lo, q1 = n01.hi, q2 = n23.lo, q3 = n23.hi;
@@ -184,32 +192,43 @@ __device__ __forceinline__ usrt_raycast_result traverse_strict(const TraceScene&
             float lentry, rentry;
             const bool lhit = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ray, &lentry);
             const bool rhit = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ray, &rentry);
-            // left child then right child (:148-175): leaves are queued in that order
-            if (lhit && (lref & 0x80000000u)) { fifo[(head + count) & (kLeafFifo - 1)][tid] = lref & 0x7FFFFFFFu; ++count; }
-            if (rhit && (rref & 0x80000000u)) { fifo[(head + count) & (kLeafFifo - 1)][tid] = rref & 0x7FFFFFFFu; ++count; }
-            const bool lgo = lhit && !(lref & 0x80000000u), rgo = rhit && !(rref & 0x80000000u);
-            if (rgo) {
-                if (lgo) stack[sp++] = lref;
-                index = rref;
-            } else if (lgo) {
-                index = lref;
-            } else if (sp != 0) {
-                index = stack[--sp];
-            } else {
-                alive = false;
+            // left child then right child (:148-175): leaves are queued in that order (leaf bit kept, cleared at the pop)
+            if (lhit && (lref & 0x80000000u)) {
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(fifo_sh + (tail & (kLeafFifo - 1)) * kSlotBytes), "r"(lref) : "memory");
+                ++tail;
             }
+            if (rhit && (rref & 0x80000000u)) {
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(fifo_sh + (tail & (kLeafFifo - 1)) * kSlotBytes), "r"(rref) : "memory");
+                ++tail;
+            }
+            const bool lgo = lhit && !(lref & 0x80000000u), rgo = rhit && !(rref & 0x80000000u);
+            // next node, written as selects (the lanes of a warp disagree here all the time): right child first,
+            // the left one deferred; with no child to enter, the youngest deferred sibling; else this lane is done
+            if (lgo && rgo) stack[sp++] = lref;
+            const bool none = !(lgo || rgo);
+            const bool pop = none && sp != 0;
+            uint32_t next = rgo ? rref : lref;
+            if (pop) next = stack[--sp];
+            finished = none && !pop;
+            index = finished ? kDone : next;
         }
-        const bool any_alive = __any_sync(0xFFFFFFFFu, alive);
+        // One vote per visit: anything to do besides walking on? (a FIFO that the next visit could overflow, or a
+        // lane that has just run out of nodes)
+        if (!__any_sync(0xFFFFFFFFu, finished || tail - head > (uint32_t)(kLeafFifo - 2))) continue;
+        walking -= __popc(__ballot_sync(0xFFFFFFFFu, finished));
         // triangle rounds: while some lane could overflow on its next visit, or to drain at the end
-        while (__any_sync(0xFFFFFFFFu, count > (uint32_t)(kLeafFifo - 2)) || (!any_alive && __any_sync(0xFFFFFFFFu, count != 0))) {
-            if (count != 0) {
-                const uint32_t leaf = fifo[head][tid];
-                head = (head + 1) & (kLeafFifo - 1); --count;
+        while (__any_sync(0xFFFFFFFFu, tail - head > (uint32_t)(kLeafFifo - 2)) ||
+               (walking == 0 && __any_sync(0xFFFFFFFFu, tail != head))) {
+            if (tail != head) {
+                uint32_t leaf;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(leaf) : "r"(fifo_sh + (head & (kLeafFifo - 1)) * kSlotBytes) : "memory");
+                leaf &= 0x7FFFFFFFu;
+                ++head;
                 const float4* t = s.packed_tris + (size_t)leaf * 3;
                 ray_triangle(ray, __ldg(t + 0), __ldg(t + 1), __ldg(t + 2), best);
             }
         }
-        if (!any_alive) break;
+        if (walking == 0) break;
     }
     return best;
 }
