@@ -155,3 +155,81 @@ def brute_force_hits(origin, direction, v0, v1, v2, tri_min, tri_max, order, max
             j = int(np.argmin(t))             # first minimum in visiting order
             out.append((t[j], int(order[j]), u[j], v[j]))
     return out
+
+
+# ---- diffuse bounce rays (BASELINE configs[4]; defined by oracle/usrt_oracle.cpp DiffuseRay) --------------------
+def primary_rays(width, height, near, tan_half_fov, cam_to_world):
+    """Raytracing.compute:108-126 + RaytracingMeshDrawer.cs:78-81, vectorised over the frame: (H*W, 3) origins
+    and unit directions, pixel index y*W + x."""
+    m = np.asarray(cam_to_world, F).reshape(4, 4)
+    near, fov = F(near), F(tan_half_fov)
+    h = F(F(F(2) * near) * fov)
+    w = F(F(F(width) * h) / F(height))
+    xs = (np.arange(width, dtype=np.uint32).astype(F) + F(0.5)).astype(F)
+    ys = (np.arange(height, dtype=np.uint32).astype(F) + F(0.5)).astype(F)
+    dx = (F(F(-w) / F(2)) + (F(w / F(width)) * xs).astype(F)).astype(F)
+    dy = (F(F(-h) / F(2)) + (F(h / F(height)) * ys).astype(F)).astype(F)
+    DX, DY = np.meshgrid(dx, dy)                        # [y][x]
+    DZ = np.full_like(DX, -near)
+    o = np.empty(3, F); d = np.empty((height, width, 3), F)
+    for r in range(3):
+        o[r] = F(F(F(m[r, 0] * F(0)) + F(m[r, 1] * F(0))) + F(m[r, 2] * F(0))) + F(m[r, 3] * F(1))
+        d[..., r] = ((((m[r, 0] * DX).astype(F) + (m[r, 1] * DY).astype(F)).astype(F) + (m[r, 2] * DZ).astype(F)).astype(F)
+                     + F(m[r, 3] * F(0))).astype(F)
+    ln = np.sqrt(_dot(d, d)).astype(F)
+    d = (d / ln[..., None]).astype(F)
+    return np.broadcast_to(o, (height * width, 3)).copy(), d.reshape(-1, 3)
+
+
+def _hash64(x):
+    x = np.asarray(x, np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x += np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def diffuse_rays(distance, triangle_index, va, vb, vc, width, height, near, tan_half_fov, cam_to_world, seed,
+                 first_sample, num_samples, max_float):
+    """Bounce rays of samples [first_sample, +num_samples): (num_samples * H * W, 8) float32, sample-major.
+    distance / triangle_index: the primary hit records; va, vb, vc: (n, 3) triangle vertices."""
+    o, d = primary_rays(width, height, near, tan_half_fov, cam_to_world)
+    frame = width * height
+    t = np.asarray(distance, F)
+    hit = t != F(max_float)
+    P = (o + (d * t[:, None]).astype(F)).astype(F)
+    ti = np.asarray(triangle_index, np.int64)
+    a, b, c = (np.asarray(v, F)[ti] for v in (va, vb, vc))
+    n = _cross((b - a).astype(F), (c - a).astype(F))
+    n2 = _dot(n, n)
+    ok = hit & (n2 > 0)
+    with np.errstate(all="ignore"):
+        n = (n / np.sqrt(n2).astype(F)[:, None]).astype(F)
+    n = np.where((_dot(n, d) > 0)[:, None], -n, n)
+    out = np.zeros((num_samples, frame, 8), F)
+    pix = np.arange(frame, dtype=np.uint64)
+    for s in range(num_samples):
+        smp = np.uint64((first_sample + s) & 0xFFFF)
+        with np.errstate(over="ignore"):
+            stream = _hash64(np.uint64(seed) ^ _hash64((pix << np.uint64(16)) | smp))
+        u = n.copy()
+        todo = np.ones(frame, bool)
+        for k in range(16):
+            with np.errstate(over="ignore"):
+                bits = _hash64(stream + np.uint64(k))
+            v = np.stack([(((bits >> np.uint64(sh)) & np.uint64(0x1FFFFF)).astype(np.uint32).astype(F) * F(2.0 ** -20)).astype(F) - F(1)
+                          for sh in (0, 21, 42)], -1).astype(F)
+            l2 = _dot(v, v)
+            acc = todo & (l2 <= F(1)) & (l2 > F(1e-4))
+            with np.errstate(all="ignore"):
+                u[acc] = (v[acc] / np.sqrt(l2[acc]).astype(F)[:, None]).astype(F)
+            todo &= ~acc
+        dd = (n + u).astype(F)
+        d2 = _dot(dd, dd)
+        with np.errstate(all="ignore"):
+            dn = (dd / np.sqrt(d2).astype(F)[:, None]).astype(F)
+        dd = np.where((d2 < F(1e-8))[:, None], n, dn)
+        out[s, :, 0:3] = np.where(ok[:, None], (P + (n * F(0.001)).astype(F)).astype(F), F(0))
+        out[s, :, 4:7] = np.where(ok[:, None], dd, F(0))
+    return out.reshape(-1, 8)

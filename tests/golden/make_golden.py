@@ -7,6 +7,7 @@ pins of the oracle -- cross-checked against the independent numpy restatement in
 so that neither the oracle nor the CUDA path can drift silently. Inputs are stored with the outputs,
 so the fixtures do not depend on the mesh generators staying bit-stable.
   small_soup.npz : 96-triangle soup, every buffer of the build + a 16x12 primary frame + 64 random rays
+                   + 2 samples of diffuse bounce rays off that frame and their hit records
   digests.json   : sha256 of every buffer for larger seeded scenes (grid 12,800; soup 65,536)
 """
 import hashlib
@@ -45,6 +46,10 @@ def main():
     out["cam_to_world"] = np.asarray(cam["cam_to_world"], np.float32)
     out["primary_16x12"] = s.trace_primary(16, 12, cam["near"], cam["tan_half_fov"], cam["cam_to_world"]).view(np.uint8)
     out["ray_hits"] = s.trace_rays(rays).view(np.uint8)
+    prim = s.trace_primary(16, 12, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    bounce = O.diffuse_rays(prim, tris, 16, 12, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], 0x601F, 0, 2)
+    out["diffuse_rays_16x12x2"] = bounce                       # BASELINE configs[4] bounce rays, seed 0x601F, samples 0-1
+    out["diffuse_hits"] = s.trace_rays(bounce).view(np.uint8)
     np.savez_compressed(os.path.join(HERE, "small_soup.npz"), **out)
 
     digests = {}

@@ -305,3 +305,18 @@ def test_diffuse_bounce_rays_properties(oracle):
     assert np.array_equal(oracle.diffuse_rays(hits, tris, *args, 77, 2, 2).reshape(2, w * h, 8), rays[2:])
     assert 0.55 < cosine.mean() < 0.78                      # cosine-weighted: E[cos] = 2/3
     assert not np.array_equal(rays[0], rays[1])
+
+
+def test_diffuse_bounce_rays_cpp_twin_equals_numpy_restatement(oracle):
+    """The two independent restatements (C++ scalar loop, vectorised numpy) of the bounce-ray generator agree
+    bit for bit, primary-ray generation included."""
+    from unitysimpleraytracing_b200 import meshes
+    for tris, cam in ((meshes.scene_c1(4096), meshes.SCENE_SOUP_CAMERA), (meshes.sphere(24, 48), meshes.REFERENCE_CAMERA)):
+        w, h = 40, 23
+        args = (w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+        hits = oracle.Scene(tris).trace_primary(*args)
+        want = oracle.diffuse_rays(hits, tris, *args, 0xABCDEF, 1, 3)
+        got = NP.diffuse_rays(hits["distance"], hits["triangleIndex"], tris["a"], tris["b"], tris["c"], *args, 0xABCDEF, 1, 3,
+                              oracle.max_float())
+        assert (hits["distance"] != oracle.max_float()).any()
+        assert got.tobytes() == want.tobytes()
