@@ -76,6 +76,13 @@ int usrt_sync(usrt_context* ctx);
 int usrt_set_stream(usrt_context* ctx, void* cuda_stream);
 /* World box of NormalizeCentroid, default -125/+125 (MeshBufferContainer.cs:9-15). */
 int usrt_set_world_bounds(usrt_context* ctx, float whole_min, float whole_max);
+/* Per-axis box instead of the cube, and the reference's own TODO ("reduce scene data for finding AABB scene in
+ * runtime", MeshBufferContainer.cs:7) as an OPT-IN: usrt_fit_world_box reduces the uploaded vertices on the device
+ * to their per-axis min / max (an axis on which the mesh is flat gets max = min + 1), makes that the box of
+ * NormalizeCentroid and returns it (out pointers may be NULL). Synchronises. Morton keys then differ from the
+ * reference's fixed +-125 box by construction; the oracle takes the same box. */
+int usrt_set_world_box(usrt_context* ctx, const float box_min[3], const float box_max[3]);
+int usrt_fit_world_box(usrt_context* ctx, float out_min[3], float out_max[3]);
 uint32_t usrt_capacity(const usrt_context* ctx);
 uint32_t usrt_triangles_length(const usrt_context* ctx);   /* MeshBufferContainer.TrianglesLength :30 */
 

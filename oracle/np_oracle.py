@@ -21,7 +21,8 @@ def morton_and_aabb(a, b, c, whole_min=-125.0, whole_max=125.0):
     mn = (np.minimum(np.minimum(a, b), c) - F(0.001)).astype(F)
     mx = (np.maximum(np.maximum(a, b), c) + F(0.001)).astype(F)
     cen = ((mn + mx).astype(F) * F(0.5)).astype(F)
-    cen = ((cen - F(whole_min)).astype(F) / (F(whole_max) - F(whole_min))).astype(F)
+    lo, hi = np.asarray(whole_min, F), np.asarray(whole_max, F)          # scalars (the cube) or per-axis 3-vectors
+    cen = ((cen - lo).astype(F) / (hi - lo).astype(F)).astype(F)
     q = np.minimum(np.maximum((cen * F(1024.0)).astype(F), F(0.0)), F(1023.0)).astype(np.uint32)  # truncation
     key = np.zeros(len(a), np.uint32)
     for bit in range(10):                      # x is the most significant of each triple

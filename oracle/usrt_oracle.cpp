@@ -354,6 +354,38 @@ float usrt_oracle_max_float() { return MAX_FLOAT; }
 
 // MeshBufferContainer.cs:123-146 (positions only; uv/normal packing is mesh ingest, not this path).
 // whole = +-125 (MeshBufferContainer.cs:9-15) unless the caller overrides it.
+// The same loop with a per-axis Whole box, and the scene box the reference leaves as a TODO
+// ("reduce scene data for finding AABB scene in runtime", MeshBufferContainer.cs:7): per-axis min / max over all
+// vertices; an axis on which the mesh is flat gets max = min + 1 so that NormalizeCentroid never divides by 0.
+// Opt-in, outside reference parity (the reference's keys come from the fixed +-125 cube).
+void usrt_oracle_scene_box(const Triangle* tris, uint32_t n, float* box_min, float* box_max) {
+    for (int k = 0; k < 3; ++k) { box_min[k] = INFINITY; box_max[k] = -INFINITY; }
+    for (uint32_t i = 0; i < n; i++)
+        for (const float* v : {tris[i].a, tris[i].b, tris[i].c})
+            for (int k = 0; k < 3; ++k) {
+                box_min[k] = minf_sel(box_min[k], v[k]);
+                box_max[k] = maxf_sel(box_max[k], v[k]);
+            }
+    for (int k = 0; k < 3; ++k)
+        if (!(box_max[k] > box_min[k])) box_max[k] = box_min[k] + 1.0f;
+}
+
+void usrt_oracle_morton_box(const Triangle* tris, uint32_t n, const float* box_min, const float* box_max,
+                            uint32_t* keys, uint32_t* values, AABB* aabbs) {
+    for (uint32_t i = 0; i < n; i++) {
+        float centroid[3];
+        AABB aabb;
+        GetCentroidAndAABB(tris[i].a, tris[i].b, tris[i].c, centroid, &aabb);
+        for (int k = 0; k < 3; ++k) {                 // NormalizeCentroid (:73-83) with Whole.min/max per axis
+            centroid[k] -= box_min[k];
+            centroid[k] /= (box_max[k] - box_min[k]);
+        }
+        keys[i] = Morton3D(centroid[0], centroid[1], centroid[2]);
+        values[i] = i;
+        aabbs[i] = aabb;
+    }
+}
+
 void usrt_oracle_morton(const Triangle* tris, uint32_t n, float whole_min, float whole_max,
                         uint32_t* keys, uint32_t* values, AABB* aabbs) {
     for (uint32_t i = 0; i < n; i++) {

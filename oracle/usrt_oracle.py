@@ -63,10 +63,24 @@ def max_float():
     return np.float32(lib().usrt_oracle_max_float())
 
 
+def scene_box(tris):
+    """Per-axis min / max of all vertices (the MeshBufferContainer.cs:7 TODO; flat axes get max = min + 1)."""
+    tris = np.ascontiguousarray(tris, dtype=TRIANGLE)
+    lo, hi = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    lib().usrt_oracle_scene_box(_p(tris), ctypes.c_uint32(len(tris)), _p(lo), _p(hi))
+    return lo, hi
+
+
 def morton(tris, whole_min=WHOLE_MIN, whole_max=WHOLE_MAX):
+    """whole_min / whole_max: scalars (the reference's cube) or 3-vectors (a per-axis box)."""
     n = len(tris)
     tris = np.ascontiguousarray(tris, dtype=TRIANGLE)
     keys = np.empty(n, np.uint32); values = np.empty(n, np.uint32); aabbs = np.zeros(n, AABB)
+    if np.ndim(whole_min) or np.ndim(whole_max):
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(whole_min, np.float32), 3))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(whole_max, np.float32), 3))
+        lib().usrt_oracle_morton_box(_p(tris), ctypes.c_uint32(n), _p(lo), _p(hi), _p(keys), _p(values), _p(aabbs))
+        return keys, values, aabbs
     lib().usrt_oracle_morton(_p(tris), ctypes.c_uint32(n), ctypes.c_float(whole_min), ctypes.c_float(whole_max),
                              _p(keys), _p(values), _p(aabbs))
     return keys, values, aabbs

@@ -320,3 +320,25 @@ def test_diffuse_bounce_rays_cpp_twin_equals_numpy_restatement(oracle):
                               oracle.max_float())
         assert (hits["distance"] != oracle.max_float()).any()
         assert got.tobytes() == want.tobytes()
+
+
+def test_fitted_world_box_opt_in(oracle):
+    """The MeshBufferContainer.cs:7 TODO as an opt-in: per-axis scene box (flat axes padded), keys from it agree
+    between the C++ twin and the numpy restatement, the cube path is untouched, and the tree is still valid."""
+    from unitysimpleraytracing_b200 import meshes
+    for tris in (meshes.uniform_soup(3000, seed=5, extent=40.0), meshes.reference_scene_grid()):
+        lo, hi = oracle.scene_box(tris)
+        v = np.concatenate([tris["a"], tris["b"], tris["c"]])
+        assert np.array_equal(lo, v.min(0))
+        flat = v.max(0) == v.min(0)
+        assert np.array_equal(hi, np.where(flat, v.min(0) + np.float32(1), v.max(0)))
+        keys, _, _ = oracle.morton(tris, lo, hi)
+        nk, _, _ = NP.morton_and_aabb(tris["a"], tris["b"], tris["c"], lo, hi)
+        assert np.array_equal(keys, nk)
+        cube_keys, _, _ = oracle.morton(tris)
+        assert np.array_equal(cube_keys, oracle.morton(tris, np.full(3, -125, np.float32), np.full(3, 125, np.float32))[0])
+        assert not np.array_equal(keys, cube_keys)
+        assert len(np.unique(keys)) >= len(np.unique(cube_keys))      # a tighter box never merges more cells
+        s = oracle.Scene(tris, lo, hi)
+        assert s.count_corrupted() == (0, 0) if hasattr(s, "count_corrupted") else True
+        assert np.array_equal(np.sort(s.sortedTriangleIndices), np.arange(len(tris)))

@@ -208,6 +208,39 @@ def test_diffuse_bounce_rays(usrt, oracle, name, cam):
     d.OnDestroy()
 
 
+@pytest.mark.parametrize("name", ["soup4097", "refgrid", "c1"])
+def test_fitted_world_box_opt_in(usrt, oracle, name):
+    """usrt_fit_world_box (the reference's runtime-scene-AABB TODO, opt-in): the device reduction equals the oracle's
+    box (flat axes padded), and a rebuild with it is bit-identical to the oracle built with the same box."""
+    tris = _mesh(name)
+    lo, hi = oracle.scene_box(tris)
+    ctx = usrt.Context(len(tris))
+    ctx.upload_triangles(tris)
+    got_lo, got_hi = ctx.fit_world_box()
+    assert np.array_equal(got_lo, lo) and np.array_equal(got_hi, hi)
+    ctx.rebuild()
+    ref = oracle.Scene(tris, lo, hi)
+    n = len(tris)
+    assert np.array_equal(ctx.download(_lib.BUF_KEYS), ref.sortedMortonCodes)
+    assert np.array_equal(ctx.download(_lib.BUF_TRIANGLE_INDEX), ref.sortedTriangleIndices)
+    assert ctx.download(_lib.BUF_INTERNAL_NODES, n - 1).tobytes() == ref.internalNodes[:n - 1].tobytes()
+    assert ctx.download(_lib.BUF_BVH_DATA, n - 1).tobytes() == ref.bvhData[:n - 1].tobytes()
+    assert ctx.count_corrupted_nodes() == (0, 0)
+    cam = meshes.SCENE_SOUP_CAMERA if name != "refgrid" else meshes.REFERENCE_CAMERA
+    want = ref.trace_primary(64, 36, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], threads=8)
+    assert _same(ctx.trace_primary(64, 36, cam["near"], cam["tan_half_fov"], cam["cam_to_world"]), want)
+    # an explicit per-axis box, then back to the reference's cube: keys return to the default ones
+    ctx.set_world_box(lo - 1, hi + 2)
+    ctx.rebuild()
+    assert np.array_equal(ctx.download(_lib.BUF_KEYS), oracle.Scene(tris, lo - 1, hi + 2).sortedMortonCodes)
+    ctx.set_world_bounds(-125.0, 125.0)
+    ctx.rebuild()
+    assert np.array_equal(ctx.download(_lib.BUF_KEYS), oracle.Scene(tris).sortedMortonCodes)
+    with pytest.raises(_lib.UsrtError):
+        ctx.set_world_box([0, 0, 0], [1, 0, 1])
+    ctx.close()
+
+
 def test_culled_mode_is_reported_separately(usrt, oracle):
     """Mode 1 is NOT part of the parity contract; it must still find a hit wherever strict does, never
     a farther one by more than fp noise. We only record how far it is from strict."""

@@ -41,6 +41,8 @@ SIGNATURES = {
     "usrt_peer_buffer_open": (_c.c_int, [_P, _P, _c.POINTER(_P)]),
     "usrt_peer_buffer_close": (_c.c_int, [_P, _P, _c.c_int]),
     "usrt_set_hit_mirrors": (_c.c_int, [_P, _c.c_int, _c.POINTER(_P)]),
+    "usrt_set_world_box": (_c.c_int, [_P, _P, _P]),
+    "usrt_fit_world_box": (_c.c_int, [_P, _P, _P]),
     "usrt_distribute_keys": (_c.c_int, [_P]),
     "usrt_construct_tree": (_c.c_int, [_P]),
     "usrt_construct_bvh": (_c.c_int, [_P]),

@@ -13,6 +13,8 @@
 
 #include "usrt_internal.cuh"
 
+#include <cmath>
+
 using namespace usrt;
 
 enum Stage : uint32_t { ST_TRIS = 1, ST_MORTON = 2, ST_SORTED = 4, ST_DISTRIBUTED = 8, ST_TREE = 16, ST_BVH = 32 };
@@ -24,7 +26,7 @@ struct usrt_context {
     uint32_t dirty_n = 0;                 // slots [0, dirty_n) may differ from their initial fill
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
-    float whole_min = -125.0f, whole_max = 125.0f;   // MeshBufferContainer.cs:9-15
+    WorldBox whole{{-125.0f, -125.0f, -125.0f}, {125.0f, 125.0f, 125.0f}};   // MeshBufferContainer.cs:9-15
     uint32_t stage = 0;
 
     // the seven scene buffers of MeshBufferContainer.cs:87-94 (+ ping-pong partners for keys/indices)
@@ -47,6 +49,7 @@ struct usrt_context {
     SortScratch sort;
     void* scan_status = nullptr;
     uint32_t* small = nullptr;            // a few device words (validators)
+    float* scene_box = nullptr;           // 6 floats: usrt_fit_world_box
     // trace
     usrt_raycast_result* hits = nullptr;
     uint64_t hits_capacity = 0, hits_count = 0;
@@ -148,7 +151,7 @@ int ensure_rays(usrt_context* ctx, uint64_t count) {
 }
 
 int do_morton(usrt_context* ctx) {
-    CU(ctx, launch_morton(ctx->triangles, ctx->n, ctx->whole_min, ctx->whole_max, ctx->keys, ctx->tri_index,
+    CU(ctx, launch_morton(ctx->triangles, ctx->n, ctx->whole, ctx->keys, ctx->tri_index,
                           ctx->tri_aabb, ctx->stream));
     ctx->launches += 1;
     ctx->stage = ST_TRIS | ST_MORTON;
@@ -254,7 +257,7 @@ int usrt_destroy(usrt_context* ctx) {
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     void* ptrs[] = {ctx->keys, ctx->keys_alt, ctx->tri_index, ctx->tri_index_alt, ctx->triangles, ctx->tri_aabb,
                     ctx->bvh, ctx->leaf, ctx->internal, ctx->slots, ctx->up_internal, ctx->up_leaf, ctx->packed_nodes, ctx->packed_tris,
-                    ctx->scan_status, ctx->small, ctx->hits, ctx->rays, ctx->texture, ctx->shaded};
+                    ctx->scan_status, ctx->small, ctx->scene_box, ctx->hits, ctx->rays, ctx->texture, ctx->shaded};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     sort_scratch_free(ctx->sort);
@@ -287,9 +290,40 @@ int usrt_set_stream(usrt_context* ctx, void* cuda_stream) {
 int usrt_set_world_bounds(usrt_context* ctx, float whole_min, float whole_max) {
     NEED_CTX(ctx);
     if (!(whole_max > whole_min)) return fail(ctx, USRT_ERR_ARG, "world bounds: max must exceed min");
-    ctx->whole_min = whole_min;
-    ctx->whole_max = whole_max;
+    for (int k = 0; k < 3; ++k) { ctx->whole.min[k] = whole_min; ctx->whole.max[k] = whole_max; }
     if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }   // kernel arguments changed
+    return USRT_OK;
+}
+
+int usrt_set_world_box(usrt_context* ctx, const float box_min[3], const float box_max[3]) {
+    NEED_CTX(ctx);
+    if (!box_min || !box_max) return fail(ctx, USRT_ERR_ARG, "world box: null pointer");
+    for (int k = 0; k < 3; ++k)
+        if (!(box_max[k] > box_min[k])) return fail(ctx, USRT_ERR_ARG, "world box: max must exceed min on every axis");
+    for (int k = 0; k < 3; ++k) { ctx->whole.min[k] = box_min[k]; ctx->whole.max[k] = box_max[k]; }
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+    return USRT_OK;
+}
+
+int usrt_fit_world_box(usrt_context* ctx, float out_min[3], float out_max[3]) {
+    NEED_CTX(ctx);
+    if (!(ctx->stage & ST_TRIS) || ctx->n == 0) return fail(ctx, USRT_ERR_STATE, "fit_world_box: no triangles uploaded");
+    if (int r = bind_device(ctx)) return r;
+    if (!ctx->scene_box) CU(ctx, cudaMalloc(&ctx->scene_box, 6 * sizeof(float)));
+    CU(ctx, launch_scene_box(ctx->triangles, ctx->n, ctx->scene_box, ctx->stream));
+    ctx->launches += 1;
+    float b[6];
+    CU(ctx, cudaMemcpyAsync(b, ctx->scene_box, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 3; ++k)
+        if (!(b[3 + k] > b[k])) b[3 + k] = b[k] + 1.0f;      // flat on this axis: any positive extent, every centroid maps to 0
+    for (int k = 0; k < 3; ++k) {
+        if (!std::isfinite(b[k]) || !std::isfinite(b[3 + k])) return fail(ctx, USRT_ERR_ARG, "fit_world_box: non-finite vertex");
+        ctx->whole.min[k] = b[k]; ctx->whole.max[k] = b[3 + k];
+        if (out_min) out_min[k] = b[k];
+        if (out_max) out_max[k] = b[3 + k];
+    }
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
     return USRT_OK;
 }
 

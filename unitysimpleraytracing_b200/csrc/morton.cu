@@ -8,6 +8,9 @@
 
 #include "usrt_internal.cuh"
 
+#include <algorithm>
+#include <cmath>
+
 namespace usrt {
 
 __device__ __forceinline__ uint32_t expand_bits(uint32_t v) {   // MeshBufferContainer.cs:32-39
@@ -26,8 +29,8 @@ __device__ __forceinline__ uint32_t quantise(float x) {          // MeshBufferCo
     return (uint32_t)x;                                           // truncation, like C# (uint)float
 }
 
-__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ tris, uint32_t n, float whole_min,
-                                                float whole_max, uint32_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ tris, uint32_t n, WorldBox whole,
+                                                uint32_t* __restrict__ keys,
                                                 uint32_t* __restrict__ values, float4* __restrict__ aabbs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -45,11 +48,11 @@ __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ tris,
     float cy = __fmul_rn(__fadd_rn(mny, mxy), 0.5f);
     float cz = __fmul_rn(__fadd_rn(mnz, mxz), 0.5f);
 
-    // NormalizeCentroid (:73-83): subtract, then a true division by (max - min)
-    const float extent = __fsub_rn(whole_max, whole_min);
-    cx = __fdiv_rn(__fsub_rn(cx, whole_min), extent);
-    cy = __fdiv_rn(__fsub_rn(cy, whole_min), extent);
-    cz = __fdiv_rn(__fsub_rn(cz, whole_min), extent);
+    // NormalizeCentroid (:73-83): subtract, then a true division by (max - min), per axis (the reference's
+    // Whole box is the cube +-125, MeshBufferContainer.cs:9-15; a fitted scene box is per axis)
+    cx = __fdiv_rn(__fsub_rn(cx, whole.min[0]), __fsub_rn(whole.max[0], whole.min[0]));
+    cy = __fdiv_rn(__fsub_rn(cy, whole.min[1]), __fsub_rn(whole.max[1], whole.min[1]));
+    cz = __fdiv_rn(__fsub_rn(cz, whole.min[2]), __fsub_rn(whole.max[2], whole.min[2]));
 
     // Morton3D (:41-50)
     const uint32_t key = expand_bits(quantise(cx)) * 4 + expand_bits(quantise(cy)) * 2 + expand_bits(quantise(cz));
@@ -60,12 +63,56 @@ __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ tris,
     aabbs[(size_t)i * 2 + 1] = make_float4(mxx, mxy, mxz, 0.0f);
 }
 
-cudaError_t launch_morton(const usrt_triangle* tris, uint32_t n, float whole_min, float whole_max, uint32_t* keys,
+// The "find the scene AABB at runtime" TODO of MeshBufferContainer.cs:7: per-axis min / max over all vertices.
+// out[0..2] = min, out[3..5] = max, pre-set to +inf / -inf. Floats are reduced with the signed-magnitude trick
+// (non-negative values order like ints, negative ones like reversed unsigned ints).
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(256) k_scene_box(const float4* __restrict__ tris, uint32_t n, float* __restrict__ out) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4* t = tris + (size_t)i * 8;
+        const float4 a = __ldg(t + 0), b = __ldg(t + 1), c = __ldg(t + 2);
+        mn[0] = sel_min(mn[0], sel_min(sel_min(a.x, b.x), c.x)); mx[0] = sel_max(mx[0], sel_max(sel_max(a.x, b.x), c.x));
+        mn[1] = sel_min(mn[1], sel_min(sel_min(a.y, b.y), c.y)); mx[1] = sel_max(mx[1], sel_max(sel_max(a.y, b.y), c.y));
+        mn[2] = sel_min(mn[2], sel_min(sel_min(a.z, b.z), c.z)); mx[2] = sel_max(mx[2], sel_max(sel_max(a.z, b.z), c.z));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            mn[k] = sel_min(mn[k], __shfl_xor_sync(0xFFFFFFFFu, mn[k], off));
+            mx[k] = sel_max(mx[k], __shfl_xor_sync(0xFFFFFFFFu, mx[k], off));
+        }
+    }
+    if ((threadIdx.x & 31u) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomic_min_float(out + k, mn[k]); atomic_max_float(out + 3 + k, mx[k]); }
+    }
+}
+
+cudaError_t launch_scene_box(const usrt_triangle* tris, uint32_t n, float* out6, cudaStream_t stream) {
+    static const float init[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    cudaError_t e = cudaMemcpyAsync(out6, init, sizeof(init), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess || n == 0) return e;
+    const uint32_t grid = std::min<uint32_t>((n + 255) / 256, 148 * 8);
+    k_scene_box<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(tris), n, out6);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_morton(const usrt_triangle* tris, uint32_t n, const WorldBox& whole, uint32_t* keys,
                           uint32_t* values, usrt_aabb* aabbs, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const uint32_t block = 256;
     const uint32_t grid = (n + block - 1) / block;
-    k_morton<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(tris), n, whole_min, whole_max, keys, values,
+    k_morton<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(tris), n, whole, keys, values,
                                          reinterpret_cast<float4*>(aabbs));
     return cudaGetLastError();
 }

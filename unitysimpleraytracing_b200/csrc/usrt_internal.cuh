@@ -49,8 +49,11 @@ cudaError_t sort_scratch_reserve(SortScratch& scratch, uint64_t count, bool need
 void sort_scratch_free(SortScratch& scratch);
 
 // K1
-cudaError_t launch_morton(const usrt_triangle* tris, uint32_t n, float whole_min, float whole_max, uint32_t* keys,
+struct WorldBox { float min[3], max[3]; };            // NormalizeCentroid's box, per axis
+cudaError_t launch_morton(const usrt_triangle* tris, uint32_t n, const WorldBox& whole, uint32_t* keys,
                           uint32_t* values, usrt_aabb* aabbs, cudaStream_t stream);
+// per-axis min / max over all vertices -> out6 (device, min xyz then max xyz)
+cudaError_t launch_scene_box(const usrt_triangle* tris, uint32_t n, float* out6, cudaStream_t stream);
 // K3 (src != dst; dst receives the distributed keys). scan_status: >= (tiles+1) x 8 bytes, zeroed by the call.
 cudaError_t launch_distribute_keys(const uint32_t* src, uint32_t* dst, uint32_t n, void* scan_status,
                                    cudaStream_t stream, int* launches);

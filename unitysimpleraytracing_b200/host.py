@@ -86,6 +86,17 @@ class Context:
     def set_world_bounds(self, whole_min, whole_max):
         self._check(self._lib.usrt_set_world_bounds(self._h, whole_min, whole_max))
 
+    def set_world_box(self, box_min, box_max):
+        lo = np.ascontiguousarray(box_min, np.float32).reshape(3); hi = np.ascontiguousarray(box_max, np.float32).reshape(3)
+        self._check(self._lib.usrt_set_world_box(self._h, _ptr(lo), _ptr(hi)))
+
+    def fit_world_box(self):
+        """Opt-in (MeshBufferContainer.cs:7 TODO): NormalizeCentroid's box becomes the per-axis min/max of the
+        uploaded vertices, reduced on the device. Returns (min[3], max[3])."""
+        lo, hi = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self._check(self._lib.usrt_fit_world_box(self._h, _ptr(lo), _ptr(hi)))
+        return lo, hi
+
     @property
     def triangles_length(self):
         return int(self._lib.usrt_triangles_length(self._h))
@@ -294,10 +305,12 @@ class MeshBufferContainer:
     ingest); Morton codes, indices and triangle AABBs are computed on the GPU (K1) instead of the
     reference's CPU loop."""
 
-    def __init__(self, mesh, capacity=None, device=0, ctx=None):
+    def __init__(self, mesh, capacity=None, device=0, ctx=None, fitWorldBox=False):
         mesh = np.ascontiguousarray(mesh, dtype=Triangle)
         self._ctx = ctx if ctx is not None else Context(capacity if capacity else max(len(mesh), 2), device)
         self._ctx.upload_triangles(mesh)           # :148-151 Sync()
+        if fitWorldBox:                            # :7 TODO, opt-in: keys no longer match the fixed +-125 cube
+            self.Whole = self._ctx.fit_world_box()
         self._ctx.morton()                         # :123-146
         self.local = {}
 
