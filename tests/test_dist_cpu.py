@@ -158,3 +158,54 @@ def test_shard_rows_cover_the_frame_exactly_once():
         seen = np.sort(seen[seen >= 0])
         assert np.array_equal(seen, np.arange(H))
         assert len({udist.shard_layout(H, world, br) for _ in range(2)}) == 1
+
+
+class _FakePeerCtx:
+    """Stands in for the CUDA context in map_peer_buffers: handles are the rank number, mapping can be made to fail."""
+
+    def __init__(self, rank, fail_create_on=None, fail_open_on=None):
+        self.rank, self.fail_create_on, self.fail_open_on = rank, fail_create_on, fail_open_on
+        self.live = set()
+
+    def peer_buffer_create(self, nbytes):
+        if self.rank == self.fail_create_on:
+            raise RuntimeError("out of memory")
+        self.live.add(("own", self.rank))
+        return 1000 + self.rank, bytes([self.rank]) * 64
+
+    def peer_buffer_open(self, handle):
+        if self.rank == self.fail_open_on:
+            raise RuntimeError("no peer access")
+        self.live.add(("peer", handle[0]))
+        return 2000 + handle[0]
+
+    def peer_buffer_close(self, ptr, opened):
+        self.live.discard(("peer", ptr - 2000) if opened else ("own", ptr - 1000))
+
+
+def _peer_map_worker(rank, world, port, mode, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = _FakePeerCtx(rank, fail_create_on=1 if mode == "create" else None, fail_open_on=2 if mode == "open" else None)
+    try:
+        own, peers = udist.map_peer_buffers(ctx, 4096, device="cpu")
+        res = ("ok", own, peers)
+    except RuntimeError as e:
+        res = ("raised", str(e), sorted(ctx.live))
+    np.save(os.path.join(out_dir, "m%d.npy" % rank), np.array([repr(res)]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["fine", "create", "open"])
+def test_peer_buffer_mapping_is_collectively_consistent(tmp_path, mode):
+    """map_peer_buffers: every rank gets every rank's buffer, or -- when ANY rank cannot allocate or map -- every
+    rank raises, nothing stays allocated or mapped, and no rank is left waiting in a collective."""
+    world = 3
+    mp.spawn(_peer_map_worker, args=(world, _free_port(), mode, str(tmp_path)), nprocs=world, join=True)
+    res = [eval(str(np.load(tmp_path / ("m%d.npy" % r))[0])) for r in range(world)]
+    if mode == "fine":
+        for r, (tag, own, peers) in enumerate(res):
+            assert tag == "ok" and own == 1000 + r
+            assert peers == [1000 + q if q == r else 2000 + q for q in range(world)]
+    else:
+        assert all(t[0] == "raised" and t[2] == [] for t in res), res

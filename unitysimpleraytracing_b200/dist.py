@@ -54,7 +54,7 @@ def assemble_frame(gathered, width, height, num_shards, block_rows=8):
     return out.reshape((height * width,) + g.shape[3:])
 
 
-def map_peer_buffers(ctx, nbytes, group=None):
+def map_peer_buffers(ctx, nbytes, group=None, device=None):
     """Allocate `nbytes` on this rank's GPU and map every other rank's buffer of the same call into this process
     (CUDA IPC over torch.distributed). Returns (own_ptr, [ptr of rank 0's buffer, ...]) with own_ptr at index
     rank. Collective, and collectively consistent: if any rank cannot allocate or map (no peer access, separate
@@ -62,7 +62,9 @@ def map_peer_buffers(ctx, nbytes, group=None):
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    device = torch.device("cuda", torch.cuda.current_device())
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    on_gpu = torch.device(device).type == "cuda"
 
     def everyone(ok):
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
@@ -94,7 +96,8 @@ def map_peer_buffers(ctx, nbytes, group=None):
         for r in range(world):
             if r != rank and peer_ptr[r]:
                 ctx.peer_buffer_close(peer_ptr[r], True)
-        torch.cuda.synchronize()
+        if on_gpu:
+            torch.cuda.synchronize()
         dist.barrier(group=group)                                      # nobody frees a buffer a peer still maps
         ctx.peer_buffer_close(own_ptr, False)
         raise RuntimeError("map_peer_buffers: CUDA IPC mapping failed on some rank (this rank: %s)" % err)
