@@ -70,3 +70,31 @@ def test_bvh_file_round_trip_on_host(tmp_path, oracle):
     for k in bufs:
         assert back[k].tobytes() == np.ascontiguousarray(bufs[k]).tobytes()
     assert os.path.getsize(path) == 48 + n * (4 + 4 + 128 + 32 + 8) + (n - 1) * (32 + 24)
+
+
+def test_multiple_meshes_merge_and_map_back():
+    """MeshBufferContainer.cs:96 "TODO multiple meshes": merged scene + the map from a hit's triangleIndex back to
+    (mesh, local triangle). The container's constructor is exercised with a stand-in context (no GPU here)."""
+    from unitysimpleraytracing_b200 import host, meshes
+    from unitysimpleraytracing_b200.scene_types import Triangle
+    a, b, c = meshes.uniform_soup(5, seed=1), meshes.sphere(4, 8), meshes.uniform_soup(1, seed=2)
+    merged, off = host.merge_meshes([a, b, c])
+    assert merged.dtype == Triangle and len(merged) == len(a) + len(b) + len(c)
+    assert off.tolist() == [0, 5, 5 + len(b), 6 + len(b)]
+    assert merged[:5].tobytes() == a.tobytes() and merged[5:5 + len(b)].tobytes() == b.tobytes() and merged[-1:].tobytes() == c.tobytes()
+    mesh, local = host.mesh_of_triangle(off, [0, 4, 5, 5 + len(b) - 1, 5 + len(b)])
+    assert mesh.tolist() == [0, 0, 1, 1, 2] and local.tolist() == [0, 4, 0, len(b) - 1, 0]
+
+    class FakeCtx:
+        def __init__(self): self.calls = []
+        def upload_triangles(self, t): self.calls.append(("upload", len(t), t.tobytes()))
+        def morton(self): self.calls.append(("morton",))
+        def fit_world_box(self): self.calls.append(("fit",)); return (np.zeros(3, np.float32), np.ones(3, np.float32))
+
+    ctx = FakeCtx()
+    cont = host.MeshBufferContainer([a, b, c], ctx=ctx, fitWorldBox=True)
+    assert [x[0] for x in ctx.calls] == ["upload", "fit", "morton"] and ctx.calls[0][2] == merged.tobytes()
+    assert cont.MeshOffsets.tolist() == off.tolist()
+    assert [x.tolist() for x in cont.MeshOfTriangle([6])] == [[1], [1]]
+    single = host.MeshBufferContainer(a, ctx=FakeCtx())
+    assert single.MeshOffsets.tolist() == [0, 5] and [x.tolist() for x in single.MeshOfTriangle([3])] == [[0], [3]]

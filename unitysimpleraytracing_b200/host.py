@@ -300,12 +300,34 @@ class DeviceBuffer:
         return self.ctx.download(self.buffer, count)
 
 
+def merge_meshes(meshes):
+    """Several Triangle arrays -> (one Triangle array, offsets[len(meshes) + 1]): mesh k owns the triangle indices
+    [offsets[k], offsets[k + 1]) of the merged scene (the "TODO multiple meshes" of MeshBufferContainer.cs:96)."""
+    parts = [np.ascontiguousarray(m, dtype=Triangle).reshape(-1) for m in meshes]
+    offsets = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int64)
+    merged = np.concatenate(parts) if parts else np.zeros(0, Triangle)
+    return merged, offsets
+
+
+def mesh_of_triangle(offsets, triangle_index):
+    """(mesh id, triangle index inside that mesh) of merged-scene triangle indices (e.g. hit records'
+    triangleIndex); vectorised."""
+    idx = np.asarray(triangle_index, np.int64)
+    mesh = np.searchsorted(np.asarray(offsets, np.int64), idx, side="right") - 1
+    return mesh, idx - np.asarray(offsets, np.int64)[mesh]
+
+
 class MeshBufferContainer:
     """Assets/_Scripts/MeshBufferContainer.cs. `mesh` is Triangle[n] (the packing loop :117-146 is mesh
-    ingest); Morton codes, indices and triangle AABBs are computed on the GPU (K1) instead of the
-    reference's CPU loop."""
+    ingest) or a list of such arrays (:96 "TODO multiple meshes": they are merged into one scene and
+    `MeshOffsets` / `MeshOfTriangle` map hit records back); Morton codes, indices and triangle AABBs are
+    computed on the GPU (K1) instead of the reference's CPU loop."""
 
     def __init__(self, mesh, capacity=None, device=0, ctx=None, fitWorldBox=False):
+        if isinstance(mesh, (list, tuple)):
+            mesh, self.MeshOffsets = merge_meshes(mesh)
+        else:
+            self.MeshOffsets = np.array([0, len(mesh)], np.int64)
         mesh = np.ascontiguousarray(mesh, dtype=Triangle)
         self._ctx = ctx if ctx is not None else Context(capacity if capacity else max(len(mesh), 2), device)
         self._ctx.upload_triangles(mesh)           # :148-151 Sync()
@@ -325,6 +347,9 @@ class MeshBufferContainer:
     BvhData = property(lambda s: DeviceBuffer(s._ctx, _lib.BUF_BVH_DATA))              # :22
     BvhLeafNode = property(lambda s: DeviceBuffer(s._ctx, _lib.BUF_LEAF_NODES))        # :23
     BvhInternalNode = property(lambda s: DeviceBuffer(s._ctx, _lib.BUF_INTERNAL_NODES))  # :24
+
+    def MeshOfTriangle(self, triangleIndex):
+        return mesh_of_triangle(self.MeshOffsets, triangleIndex)
 
     @property
     def TrianglesLength(self):                     # :30
