@@ -172,7 +172,8 @@ int usrt_trace_primary_async(usrt_context* ctx, int width, int height, float nea
  * blocks b (block = block_rows consecutive rows) with b % S == s -- interleaved for load balance -- in
  * ONE launch and writes them compactly: local row lr = (b / S) * block_rows + row_in_block, record
  * index lr * width + x. Every shard's buffer has ceil(ceil(H / block_rows) / S) * block_rows rows
- * (equal sizes for an all-gather); rows that fall outside the frame are zero-filled. dev_out may be
+ * (equal sizes for an all-gather); rows that fall outside the frame hold MISS records
+ * { (float)0x7F7FFFFF, 0, (0,0) }. dev_out may be
  * NULL (the context's hit buffer is used, see usrt_hits_device); host_out may be NULL. */
 int usrt_trace_primary_sharded(usrt_context* ctx, int width, int height, float near_plane, float tan_half_fov,
                                const float camera_to_world[16], int block_rows, int shard, int num_shards,
@@ -202,8 +203,12 @@ int usrt_set_trace_mode(usrt_context* ctx, int mode);
 /* Install the seven scene buffers of MeshBufferContainer.cs:87-94 from HOST arrays in the reference's
  * layouts (n triangles: n keys / indices / triangles / triangle AABBs / leaf nodes, n-1 node AABBs and
  * internal nodes) -- a tree that was built elsewhere: a dump of this library, or the buffers the
- * reference's own kernels produced. The traversal-side arrays are derived on the device; afterwards the
- * context traces exactly as if it had built the tree itself. Synchronous. */
+ * reference's own kernels produced. The input is treated as UNTRUSTED: child / leaf / triangle indices are range-
+ * checked on the device, every node must have exactly one parent, and every leaf must reach node 0 within 64 levels
+ * (the depth of the traversal stack, Raytracing.compute:133); otherwise USRT_ERR_ARG and the context holds no scene.
+ * The traversal-side arrays are derived on the device; afterwards the context traces exactly as if it had built the
+ * tree itself, and usrt_construct_bvh may re-fit it (when every leaf sits in its own slot, as TreeConstructor's do;
+ * else USRT_ERR_STATE). Synchronous. */
 int usrt_upload_bvh(usrt_context* ctx, uint32_t n, const uint32_t* keys, const uint32_t* triangle_index,
                     const usrt_triangle* triangles, const usrt_aabb* triangle_aabb, const usrt_aabb* bvh_data,
                     const usrt_leaf_node* leaf_nodes, const usrt_internal_node* internal_nodes);

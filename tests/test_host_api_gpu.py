@@ -213,3 +213,101 @@ def test_rebuild_graph_replay_and_legacy_stream_fallback(usrt, oracle):
     ctx.rebuild(); ctx.rebuild()
     assert ctx.download(_lib.BUF_BVH_DATA, 4999).tobytes() == ra.bvhData[:4999].tobytes()
     ctx.close()
+
+
+def test_rebuild_graph_survives_a_larger_standalone_sort(usrt, oracle):
+    """The captured rebuild graph points into the sort scratch; a standalone sort of more pairs than the context was
+    created for re-allocates that scratch, so the next rebuild must re-capture (not replay into freed memory)."""
+    tris = meshes.uniform_soup(6000, seed=21)
+    ref = oracle.Scene(tris)
+    ctx = usrt.Context(6000)
+    ctx.upload_triangles(tris)
+    ctx.rebuild(); ctx.rebuild()                                  # second call replays the graph
+    rng = np.random.default_rng(5)
+    k = rng.integers(0, 2 ** 32, 3_000_000, dtype=np.uint64).astype(np.uint32); v = np.arange(len(k), dtype=np.uint32)
+    order = np.argsort(k, kind="stable")
+    ctx.sort_pairs_host(k, v)                                     # needs 500x the status words: scratch is re-allocated
+    assert np.array_equal(v, order.astype(np.uint32))
+    for _ in range(3):
+        ctx.rebuild()
+        ctx.sync()
+    assert ctx.download(_lib.BUF_BVH_DATA, 5999).tobytes() == ref.bvhData[:5999].tobytes()
+    assert np.array_equal(ctx.download(_lib.BUF_KEYS), ref.sortedMortonCodes)
+    assert ctx.count_corrupted_nodes() == (0, 0)
+    ctx.close()
+
+
+def _oracle_bvh(ref, tris):
+    return dict(keys=ref.sortedMortonCodes, triangleIndex=ref.sortedTriangleIndices, triangleData=tris,
+                triangleAABB=ref.triangleAABB, bvhData=ref.bvhData, leafNodes=ref.leafNodes, internalNodes=ref.internalNodes)
+
+
+def test_refit_after_import_uses_rebuilt_links(usrt, oracle):
+    """usrt_upload_bvh derives the K4 -> K5 parent links itself, so ConstructBVH on an imported tree (here with every
+    node box wiped first) reproduces the oracle's boxes and traces identically."""
+    from unitysimpleraytracing_b200 import bvh_io
+    tris = meshes.uniform_soup(5000, seed=22)
+    ref = oracle.Scene(tris)
+    n = len(tris)
+    bufs = _oracle_bvh(ref, tris)
+    bufs["bvhData"] = np.zeros_like(ref.bvhData)                  # boxes are what the refit must recompute
+    ctx = usrt.Context(n)
+    bvh_io.upload_bvh(ctx, n, bufs)
+    for _ in range(2):                                            # re-runnable
+        ctx.construct_bvh()
+        assert ctx.download(_lib.BUF_BVH_DATA, n - 1).tobytes() == ref.bvhData[:n - 1].tobytes()
+    rays = meshes.incoherent_rays(1500, seed=23)
+    assert ctx.trace_rays(rays).tobytes() == ref.trace_rays(rays).tobytes()
+    ctx.close()
+
+
+@pytest.mark.parametrize("damage", ["child_out_of_range", "two_parents", "cycle", "triangle_index", "bad_type", "root_as_child"])
+def test_corrupt_import_is_rejected(usrt, oracle, damage):
+    from unitysimpleraytracing_b200 import bvh_io
+    tris = meshes.uniform_soup(300, seed=24)
+    ref = oracle.Scene(tris)
+    n = len(tris)
+    bufs = {k: np.array(v, copy=True) for k, v in _oracle_bvh(ref, tris).items()}
+    nodes = bufs["internalNodes"]
+    inner = [i for i in range(1, n - 1) if nodes["leftNodeType"][i] == 0]       # nodes with an internal left child
+    if damage == "child_out_of_range":
+        nodes["rightNode"][5] = n + 3
+    elif damage == "two_parents":
+        nodes["leftNode"][inner[0]] = nodes["leftNode"][inner[1]]
+    elif damage == "cycle":                                        # a node's left child becomes one of its ancestors
+        i = [j for j in inner if nodes["parent"][j] != 0][-1]
+        a, b = int(nodes["parent"][i]), int(nodes["leftNode"][i])
+        nodes["leftNode"][i] = a
+        side = "leftNode" if nodes["leftNode"][int(nodes["parent"][a])] == a and nodes["leftNodeType"][int(nodes["parent"][a])] == 0 else "rightNode"
+        nodes[side][int(nodes["parent"][a])] = b                   # keeps "one parent each": only the depth walk can see it
+    elif damage == "triangle_index":
+        bufs["triangleIndex"][7] = 0xFFFFFFF0
+    elif damage == "bad_type":
+        nodes["leftNodeType"][3] = 7
+    elif damage == "root_as_child":
+        nodes["rightNode"][inner[0]] = 0; nodes["rightNodeType"][inner[0]] = 0
+    ctx = usrt.Context(n)
+    with pytest.raises(_lib.UsrtError) as e:
+        bvh_io.upload_bvh(ctx, n, bufs)
+    assert e.value.code == -1
+    with pytest.raises(_lib.UsrtError):                            # nothing usable was installed
+        ctx.trace_primary(4, 4, 0.3, 0.5, np.eye(4, dtype=np.float32))
+    ctx.upload_triangles(tris); ctx.rebuild()                      # the context itself is still fine
+    assert ctx.download(_lib.BUF_BVH_DATA, n - 1).tobytes() == ref.bvhData[:n - 1].tobytes()
+    ctx.close()
+
+
+def test_partial_trace_then_shade_sees_misses_not_garbage(usrt, oracle):
+    """A freshly allocated hit buffer is filled with miss records, so shading after a row-range trace never indexes
+    the triangle buffer with uninitialised triangleIndex values."""
+    tris = meshes.scene_c1(); cam = meshes.SCENE_SOUP_CAMERA
+    ctx = usrt.Context(len(tris)); ctx.upload_triangles(tris); ctx.rebuild()
+    w, h = 80, 60
+    part = ctx.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], y0=20, y1=30)
+    ctx.upload_texture(np.ones((4, 4, 4), np.float32))
+    img = ctx.shade()
+    rows = img.reshape(h, w, 4)
+    assert (rows[:20, :, 3] == 0).all() and (rows[30:, :, 3] == 0).all()          # untraced rows are misses
+    full = oracle.Scene(tris).trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    assert part[20 * w:30 * w].tobytes() == full[20 * w:30 * w].tobytes()
+    ctx.close()

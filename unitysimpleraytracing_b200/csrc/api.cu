@@ -74,6 +74,7 @@ struct usrt_context {
     cudaGraphExec_t graph_exec = nullptr;
     uint32_t graph_n = 0;
     cudaStream_t graph_stream = nullptr;
+    uint64_t graph_sort_generation = 0;   // SortScratch::generation the captured launches point into
     uint64_t graph_launches = 0;
 
     uint64_t launches = 0;
@@ -136,6 +137,10 @@ int ensure_hits(usrt_context* ctx, uint64_t count) {
         ctx->hits = nullptr; ctx->hits_capacity = 0;
         CU(ctx, cudaMalloc(&ctx->hits, count * sizeof(usrt_raycast_result)));
         ctx->hits_capacity = count;
+        // a partial trace (rows [y0,y1)) leaves the other records untouched; usrt_shade / usrt_diffuse_rays walk all of
+        // them and index the triangle buffer by triangleIndex, so fresh memory starts as misses (Raytracing.compute:129-131)
+        CU(ctx, launch_fill_miss(ctx->hits, count, ctx->stream));
+        ctx->launches += 1;
     }
     return USRT_OK;
 }
@@ -391,12 +396,29 @@ int usrt_upload_bvh(usrt_context* ctx, uint32_t n, const uint32_t* keys, const u
     CU(ctx, cudaMemcpyAsync(ctx->bvh, bvh_data, (size_t)(n - 1) * sizeof(usrt_aabb), k, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->leaf, leaf_nodes, (size_t)n * sizeof(usrt_leaf_node), k, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->internal, internal_nodes, (size_t)(n - 1) * sizeof(usrt_internal_node), k, ctx->stream));
+    // The file is untrusted: every index the traversal and the refit will follow is checked on the device first
+    // (ranges, exactly one parent per node, one tree of depth <= 64 -- the trace stack of Raytracing.compute:133).
+    ctx->n = 0;
+    ctx->stage = 0;                                        // nothing usable until the tree is accepted
+    uint32_t err[2] = {0, 0};
+    CU(ctx, launch_import_validate(n, ctx->tri_index, ctx->internal, ctx->leaf, ctx->up_internal, ctx->up_leaf, ctx->small, ctx->stream));
+    ctx->launches += 2;
+    CU(ctx, cudaMemcpyAsync(err, ctx->small, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err[0]) return fail(ctx, USRT_ERR_ARG, "upload_bvh: %u invalid node links / indices (out of range, or not one parent per node)", err[0]);
+    CU(ctx, launch_import_links(n, ctx->internal, ctx->up_internal, ctx->up_leaf, ctx->small, ctx->stream));
+    ctx->launches += 2;
+    CU(ctx, cudaMemcpyAsync(err, ctx->small, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err[0]) return fail(ctx, USRT_ERR_ARG, "upload_bvh: %u leaves do not reach node 0 within 64 levels (cycle, forest, or too deep)", err[0]);
     CU(ctx, launch_pack_traversal(n, ctx->tri_index, ctx->tri_aabb, ctx->triangles, ctx->internal, ctx->leaf, ctx->bvh,
                                   ctx->packed_nodes, ctx->packed_tris, ctx->stream));
     ctx->launches += 1;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n = n;
-    ctx->stage = ST_TRIS | ST_MORTON | ST_SORTED | ST_DISTRIBUTED | ST_TREE | ST_BVH;
+    // ConstructBVH refits by leaf slot (BVH.compute:199-208): allowed again on this tree only if every leaf sits in its
+    // own slot, as every tree of TreeConstructor does (:114-118); the K4 -> K5 links were rebuilt above.
+    ctx->stage = ST_TRIS | ST_MORTON | ST_SORTED | ST_DISTRIBUTED | ST_BVH | (err[1] == 0 ? ST_TREE : 0u);
     return USRT_OK;
 }
 
@@ -590,9 +612,12 @@ int usrt_rebuild(usrt_context* ctx) {
     // The 12 launches + 4 memsets of a rebuild are short (the whole 1M-triangle rebuild is ~0.28 ms): replay them
     // as one CUDA graph so the gaps between them are not paid on every rebuild. Re-captured when n, the
     // stream, or the world box changes.
-    if (!ctx->graph_exec || ctx->graph_n != ctx->n || ctx->graph_stream != ctx->stream) {
+    // (the captured launches hold raw pointers into the sort scratch: a standalone sort of more pairs than this
+    // context ever saw re-allocates it, which bumps sort.generation and forces a re-capture here)
+    CU(ctx, sort_scratch_reserve(ctx->sort, ctx->n, false));              // no allocation while capturing
+    if (!ctx->graph_exec || ctx->graph_n != ctx->n || ctx->graph_stream != ctx->stream ||
+        ctx->graph_sort_generation != ctx->sort.generation) {
         drop_rebuild_graph(ctx);
-        CU(ctx, sort_scratch_reserve(ctx->sort, ctx->n, false));          // no allocation while capturing
         const uint64_t before = ctx->launches;
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
@@ -618,6 +643,7 @@ int usrt_rebuild(usrt_context* ctx) {
         if (ie != cudaSuccess) return fail(ctx, USRT_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
         ctx->graph_n = ctx->n;
         ctx->graph_stream = ctx->stream;
+        ctx->graph_sort_generation = ctx->sort.generation;
         if (ctx->keys != ctx->keys_primary) std::swap(ctx->keys, ctx->keys_alt);   // capture advanced the host-side state
     }
     CU(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
@@ -767,12 +793,16 @@ int usrt_trace_primary_sharded(usrt_context* ctx, int width, int height, float n
         out = ctx->hits;
         ctx->hits_count = count;
     }
-    // rows past the frame (padding of the last block / last shard) are never traced: pre-fill with misses
-    CU(ctx, cudaMemsetAsync(out, 0, count * sizeof(usrt_raycast_result), ctx->stream));
-    // (in the mirrors only the last local block can hold such rows: y grows with the local row)
+    // rows past the frame (padding of the last block / last shard) are never traced: pre-fill them with MISS records
+    // {MAX_FLOAT, 0, (0,0)} (Raytracing.compute:129-131) -- only the last local block can hold such rows, y grows with
+    // the local row
     const uint64_t last_block = (uint64_t)(local_rows - block_rows) * (uint64_t)width;
-    for (int i = 0; i < ctx->mirrors.count; ++i)
-        CU(ctx, cudaMemsetAsync(ctx->mirrors.ptr[i] + last_block, 0, (count - last_block) * sizeof(usrt_raycast_result), ctx->stream));
+    CU(ctx, launch_fill_miss(out + last_block, count - last_block, ctx->stream));
+    ctx->launches += 1;
+    for (int i = 0; i < ctx->mirrors.count; ++i) {
+        CU(ctx, launch_fill_miss(ctx->mirrors.ptr[i] + last_block, count - last_block, ctx->stream));
+        ctx->launches += 1;
+    }
     PrimaryParams p;
     p.width = width; p.height = height; p.near_plane = near_plane; p.tan_half_fov = tan_half_fov;
     memcpy(p.m, camera_to_world, sizeof(p.m));

@@ -390,6 +390,71 @@ __global__ void __launch_bounds__(256) k_pack_traversal(uint32_t n, const uint32
     }
 }
 
+
+// ---- imported trees (usrt_upload_bvh): validation + the private K4 -> K5 parent links --------------------------
+// A dump can be corrupt or hostile: every index the traversal or the refit will follow is checked on the device
+// before the context accepts the tree. err[0] counts violations (the import is rejected), err[1] counts leaves whose
+// `index` is not their own slot (legal for Raytracing.compute:158, but BVH.compute:199-208 refits by slot, so such a
+// tree can be traced but not re-fitted).
+constexpr int kMaxImportDepth = 64;                                  // internal nodes on a root-to-leaf path (trace stack :133 holds 64)
+
+__global__ void __launch_bounds__(256) k_import_check_nodes(uint32_t n, const uint32_t* __restrict__ sorted_indices,
+                                                            const usrt_internal_node* __restrict__ internal,
+                                                            const usrt_leaf_node* __restrict__ leaf,
+                                                            uint32_t* __restrict__ ref_internal, uint32_t* __restrict__ ref_leaf,
+                                                            uint32_t* __restrict__ err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        if (__ldg(sorted_indices + i) >= n || leaf[i].index >= n) atomicAdd(err, 1u);
+        else if (leaf[i].index != i) atomicAdd(err + 1, 1u);
+    }
+    if (i + 1 < n) {
+        const usrt_internal_node nd = internal[i];
+        const uint32_t child[2] = {nd.leftNode, nd.rightNode}, type[2] = {nd.leftNodeType, nd.rightNodeType};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (type[k] == USRT_LEAF_NODE && child[k] < n) atomicAdd(ref_leaf + child[k], 1u);
+            else if (type[k] == USRT_INTERNAL_NODE && child[k] != 0 && child[k] < n - 1) atomicAdd(ref_internal + child[k], 1u);
+            else atomicAdd(err, 1u);                                   // bad type, index out of range, or the root as a child
+        }
+    }
+}
+
+// every leaf and every internal node but the root is referenced by exactly one parent; the root by none
+__global__ void __launch_bounds__(256) k_import_check_refs(uint32_t n, const uint32_t* __restrict__ ref_internal,
+                                                           const uint32_t* __restrict__ ref_leaf, uint32_t* __restrict__ err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && ref_leaf[i] != 1u) atomicAdd(err, 1u);
+    if (i + 1 < n && ref_internal[i] != (i == 0 ? 0u : 1u)) atomicAdd(err, 1u);
+}
+
+// The up links K4 would have emitted. No node is marked block-local: an imported tree need not have Karras'
+// numbering (node id inside its own leaf range), so K5 merges all of its nodes through the global exchange slots.
+__global__ void __launch_bounds__(256) k_import_links(uint32_t n, const usrt_internal_node* __restrict__ internal,
+                                                      uint32_t* __restrict__ up_internal, uint32_t* __restrict__ up_leaf) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const usrt_internal_node nd = internal[i];
+    (nd.leftNodeType == USRT_LEAF_NODE ? up_leaf : up_internal)[nd.leftNode] = i;
+    (nd.rightNodeType == USRT_LEAF_NODE ? up_leaf : up_internal)[nd.rightNode] = i | kUpRight;
+    if (i == 0) up_internal[0] = USRT_NULL;
+}
+
+// With one parent per node the links form a forest; it is one tree of bounded depth iff every leaf reaches node 0
+// within kMaxImportDepth steps (a component cut off from the root always contains a leaf, which then fails here).
+__global__ void __launch_bounds__(256) k_import_check_depth(uint32_t n, const uint32_t* __restrict__ up_internal,
+                                                            const uint32_t* __restrict__ up_leaf, uint32_t* __restrict__ err) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t link = up_leaf[j];
+    uint32_t last = USRT_NULL;
+    for (int step = 0; step < kMaxImportDepth && link != USRT_NULL; ++step) {
+        last = link & kUpParentMask;
+        link = up_internal[last];
+    }
+    if (link != USRT_NULL || last != 0u) atomicAdd(err, 1u);
+}
+
 }  // namespace
 
 cudaError_t launch_pack_traversal(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
@@ -398,6 +463,27 @@ cudaError_t launch_pack_traversal(uint32_t n, const uint32_t* sorted_indices, co
     k_pack_traversal<<<(n + 255) / 256, 256, 0, stream>>>(n, sorted_indices, reinterpret_cast<const float4*>(tri_aabb),
                                                           reinterpret_cast<const float4*>(tris), internal, leaf,
                                                           reinterpret_cast<const float4*>(bvh), packed_nodes, packed_tris);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_import_validate(uint32_t n, const uint32_t* sorted_indices, const usrt_internal_node* internal,
+                                   const usrt_leaf_node* leaf, uint32_t* up_internal, uint32_t* up_leaf, uint32_t* err2,
+                                   cudaStream_t stream) {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(err2, 0, 8, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(up_internal, 0, (size_t)n * 4, stream)) != cudaSuccess) return e;     // reference counters first,
+    if ((e = cudaMemsetAsync(up_leaf, 0, (size_t)n * 4, stream)) != cudaSuccess) return e;         // then the links themselves
+    const uint32_t grid = (n + 255) / 256;
+    k_import_check_nodes<<<grid, 256, 0, stream>>>(n, sorted_indices, internal, leaf, up_internal, up_leaf, err2);
+    k_import_check_refs<<<grid, 256, 0, stream>>>(n, up_internal, up_leaf, err2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_import_links(uint32_t n, const usrt_internal_node* internal, uint32_t* up_internal, uint32_t* up_leaf,
+                                uint32_t* err2, cudaStream_t stream) {
+    const uint32_t grid = (n + 255) / 256;
+    k_import_links<<<grid, 256, 0, stream>>>(n, internal, up_internal, up_leaf);
+    k_import_check_depth<<<grid, 256, 0, stream>>>(n, up_internal, up_leaf, err2);
     return cudaGetLastError();
 }
 

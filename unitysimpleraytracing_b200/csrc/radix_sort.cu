@@ -379,6 +379,7 @@ cudaError_t sort_scratch_reserve(SortScratch& s, uint64_t count, bool need_alt) 
     cudaError_t e;
     if (s.hist == nullptr) {
         if ((e = cudaMalloc(&s.hist, kSortPasses * kRadix * sizeof(uint32_t))) != cudaSuccess) return e;
+        ++s.generation;
     }
     const uint64_t need = kHeaderWords * 4 + kSortPasses * status_words_bytes(count);
     if (need > s.status_bytes) {
@@ -386,6 +387,7 @@ cudaError_t sort_scratch_reserve(SortScratch& s, uint64_t count, bool need_alt) 
         s.status = nullptr; s.status_bytes = 0;
         if ((e = cudaMalloc(&s.status, need)) != cudaSuccess) return e;
         s.status_bytes = need;
+        ++s.generation;
     }
     if (need_alt && count > s.alt_capacity) {
         if (s.keys_alt) cudaFree(s.keys_alt);

@@ -390,7 +390,18 @@ __global__ void __launch_bounds__(256) k_diffuse_rays(PrimaryParams p, const usr
     rays_out[i * 2 + 1] = d4;
 }
 
+__global__ void __launch_bounds__(256) k_fill_miss(float4* __restrict__ out, uint64_t count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = make_float4(max_float(), 0.0f, 0.0f, 0.0f);   // triangleIndex 0 == +0.0f bits
+}
+
 }  // namespace
+
+cudaError_t launch_fill_miss(usrt_raycast_result* out, uint64_t count, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    k_fill_miss<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(reinterpret_cast<float4*>(out), count);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p, usrt_raycast_result* out, int mode,
                                  cudaStream_t stream, const HitMirrors& mirrors) {

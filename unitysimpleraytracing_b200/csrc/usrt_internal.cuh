@@ -27,6 +27,7 @@ struct SortScratch {
     uint32_t* hist = nullptr;          // [4][256] digit histograms, then exclusive digit bases
     void* status = nullptr;            // [4 tile counters (as 64 x u32 header)] + [passes][tiles][256] look-back words
     uint64_t status_bytes = 0;
+    uint64_t generation = 0;           // bumped whenever hist / status are (re)allocated: captured graphs hold these pointers
 };
 
 // Launches enqueue on `stream`; every function returns the first CUDA error it saw.
@@ -70,6 +71,13 @@ cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, con
 cudaError_t launch_pack_traversal(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
                                   const usrt_triangle* tris, const usrt_internal_node* internal, const usrt_leaf_node* leaf,
                                   const usrt_aabb* bvh, float4* packed_nodes, float4* packed_tris, cudaStream_t stream);
+// imported trees: (1) index ranges + one parent per node, (2) the K4 -> K5 up links + "every leaf reaches node 0 within 64
+// steps". err2 (device, 2 words): [0] violations, [1] leaves whose index is not their slot. Step 2 only if err2[0] == 0.
+cudaError_t launch_import_validate(uint32_t n, const uint32_t* sorted_indices, const usrt_internal_node* internal,
+                                   const usrt_leaf_node* leaf, uint32_t* up_internal, uint32_t* up_leaf, uint32_t* err2,
+                                   cudaStream_t stream);
+cudaError_t launch_import_links(uint32_t n, const usrt_internal_node* internal, uint32_t* up_internal, uint32_t* up_leaf,
+                                uint32_t* err2, cudaStream_t stream);
 // validator (MeshBufferContainer.cs:181-195)
 cudaError_t launch_count_corrupted(const usrt_leaf_node* leaf, const usrt_internal_node* internal, uint32_t n,
                                    uint32_t* out2, cudaStream_t stream);
@@ -102,6 +110,9 @@ cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p
                                  cudaStream_t stream, const HitMirrors& mirrors);
 cudaError_t launch_trace_rays(const TraceScene& scene, const float4* rays, uint64_t num_rays, usrt_raycast_result* out,
                               int mode, cudaStream_t stream);
+
+// count miss records {MAX_FLOAT, 0, (0,0)} (Raytracing.compute:129-131)
+cudaError_t launch_fill_miss(usrt_raycast_result* out, uint64_t count, cudaStream_t stream);
 
 // diffuse bounce rays from the primary hit records (BASELINE config 5), s_count samples per pixel starting at s0;
 // ray index = (sample - s0) * W * H + pixel
