@@ -9,15 +9,14 @@
 // B200 design (not a port): the reference moves >= 32 B/pair/pass through a block-sorted
 // intermediate and three scan dispatches. Here one upfront kernel reads the keys once and builds
 // all four digit histograms (4 B/pair), and each pass is ONE kernel ("onesweep"): a tile of
-// BLOCK x IPT pairs is ranked warp by warp -- peer lanes with the same digit find each other through
-// one shared-memory atomicOr per key plus popc on lane masks (in place of the HLSL
-// WavePrefixCountBits / WavePrefixSum one-bit splits; a ballot loop and match.any were measured and
-// are 3x / 8x slower, tools/micro/match_bench.cu) -- per-digit tile offsets are chained across
-// tiles by decoupled look-back (in place of the three Scan.compute dispatches), and pairs are
-// staged in shared memory in digit order so the scatter writes coalesced runs.
+// BLOCK x IPT pairs is ranked in 16-lane groups with one returning shared-memory atomicAdd per key (in
+// place of the HLSL WavePrefixCountBits / WavePrefixSum one-bit splits; ballot loops, match.any and
+// atomicOr + read-back matching were measured and are 2x-10x slower, tools/micro/*_bench.cu) -- per-digit
+// tile offsets are chained across tiles by decoupled look-back (in place of the three Scan.compute
+// dispatches), and pairs are staged in shared memory in digit order so the scatter writes coalesced runs.
 // 16 B/pair/pass => 68 algorithmic bytes per pair. Measured: the pass kernel is bound by the SM's
-// L1/LSU data pipe (bank conflicts of the five data-dependent shared-memory accesses per key), not
-// by HBM: profiles/r01_summary.md.
+// L1/LSU data pipe (one wavefront per cycle; bank conflicts of the data-dependent shared-memory accesses
+// per key), not by HBM: profiles/r02_summary.md.
 
 #include <algorithm>
 #include <cstdlib>
@@ -38,10 +37,14 @@ template <int BLOCK, int IPT, int CTAS> struct TileCfg {
     static constexpr int kTile = BLOCK * IPT;       // pairs per tile
     static constexpr int kWarps = BLOCK / 32;
     static constexpr int kCtasPerSM = CTAS;
-    static constexpr int kMatchBytes = kWarps * kRadix * 8;
-    static_assert(BLOCK >= kRadix, "one thread per digit in the scan / look-back step");
+    static_assert(BLOCK % kRadix == 0, "whole threads per digit in the scan / look-back step");
 };
-using BigTile = TileCfg<512, 16, 2>;                // 8192 pairs
+#ifndef USRT_BIG_BLOCK                                // (tools/micro/sort_lab.cu builds other shapes side by side)
+#define USRT_BIG_BLOCK 512
+#define USRT_BIG_IPT 16
+#define USRT_BIG_CTAS 2
+#endif
+using BigTile = TileCfg<USRT_BIG_BLOCK, USRT_BIG_IPT, USRT_BIG_CTAS>;   // 8192 pairs
 using SmallTile = TileCfg<256, 8, 6>;               // 2048 pairs
 constexpr uint64_t kSmallSortLimit = 1ull << 18;    // below this many pairs use SmallTile (measured: 2^20 is faster with BigTile)
 constexpr uint32_t kHeaderWords = 64;       // tile counters live in the first 256 B of the status buffer
@@ -137,42 +140,55 @@ __global__ void __launch_bounds__(kSortPasses * kRadix) k_scan_histogram(uint32_
 }
 
 // ---- one radix pass: rank + look-back + staged stable scatter ------------------------------------
-// Shared memory per CTA (dynamic, 50.6 KB => 4 CTAs per SM):
-//   s_match [8 warps][256] x {mask, count}  16 KB   per-warp digit words (see ranking below); after
-//                                                   ranking, count is rewritten to the warp's base slot
-//   s_pairs [4096] x {key, value}           32 KB   the tile staged in digit order
-//   s_global_off[256], s_scan[8], s_tile_id
+// Shared memory per CTA (dynamic; BigTile 97 KB => 2 CTAs per SM):
+//   s_tbl  [2 x warps][256] u32        32 KB   one word per (16-lane group, digit): running count (low 16 bits) and,
+//                                              during a ranking round, the lane bits of the group (high 16 bits);
+//                                              after the scan: first tile slot of that group's keys of that digit
+//   s_pairs [tile] x {key, value}      64 KB   the tile staged in digit order
+//   s_global_off[256], s_part[H][256], s_scan[warps], s_tile_id
 //
-// Ranking ("which lanes of my warp hold my digit, and how many did earlier rounds of this warp
-// hold") replaces the HLSL WavePrefixCountBits/WavePrefixSum splits of LocalRadixSort.compute:29-91.
-// Each lane ORs its lane bit into word[digit].mask with one shared-memory atomic; after a warp sync
-// every lane reads the 64-bit word back: mask = this round's peers, count = peers of all earlier
-// rounds. The lowest peer lane then writes {0, count + popc(mask)} -- clearing the mask and
-// advancing the running count in one store. Measured on B200 this costs ~7 SM-cycles per warp-round
-// against ~25 for an 8-ballot match and ~60 for match.any (tools/micro/match_bench.cu).
+// Ranking ("how many keys of my digit precede mine in the tile") replaces the HLSL WavePrefixCountBits /
+// WavePrefixSum one-bit splits of LocalRadixSort.compute:29-91. A 16-lane group owns 16*IPT CONSECUTIVE keys of
+// the tile (round i = 16 consecutive keys) and one 256-word table. In round i every lane does ONE shared-memory
+// atomic, old = atomicAdd(&tbl[digit], lane_bit << 16 | 1): old.count is the number of keys of that digit the group
+// held in earlier rounds PLUS the lanes of this round whose atomic was serialised before mine. B200 serialises the
+// lanes of one ATOMS that hit the same address in ascending lane order (measured: tools/micro/rank3_bench.cu, zero
+// violations), so old.count is already the stable rank. That ordering is not architecturally promised, so it is
+// VERIFIED, not assumed: old.mask holds the lanes that went first, and a lane that finds a HIGHER lane there raises
+// a flag; a warp with a flag redoes its ranking with the order-independent method (read the full mask back after a
+// warp sync, rank = count - popc(mask) + popc(mask below me)). Each lane then takes its bit out again with a second
+// atomic (no return value). Cost per round of 32 keys: 5.6 SM-cycles against 12.4 for round 1's 64-bit
+// {mask,count} words (atomicOr + 64-bit read + leader write-back) and 25 / 60 for ballot / match.any matching.
 template <typename Cfg, bool kHasValues> struct PassSmem {
+    static constexpr int kTblBytes = 2 * Cfg::kWarps * kRadix * 4;
     static constexpr int kPairBytes = Cfg::kTile * (kHasValues ? 8 : 4);
-    static constexpr int kTotal = Cfg::kMatchBytes + kPairBytes + kRadix * 4 + Cfg::kWarps * 4 + 16;
+    static constexpr int kH = Cfg::kBlock / kRadix;                      // threads per digit in the scan step
+    static constexpr int kTotal = kTblBytes + kPairBytes + kRadix * 4 + kH * kRadix * 4 + Cfg::kWarps * 4 + 16;
 };
 
 // kPeer: the multi-GPU bucket exchange. Instead of one output array, every digit has its own base address
 // (key_ptrs[d] / val_ptrs[d], this rank's slice of the receive buffer of the GPU that owns bucket d, mapped
 // through CUDA IPC): the stable scatter of the pass IS the all-to-all, written straight over NVLink.
+// flags bit 0: test hook, every warp takes the order-independent ranking path.
 template <typename Cfg, typename StatusT, bool kHasValues, bool kPeer = false>
 __global__ void __launch_bounds__(Cfg::kBlock, Cfg::kCtasPerSM)
 k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ digit_base /* [256] */,
-           uint32_t* __restrict__ tile_counter, StatusT* __restrict__ status /* [tiles][256], zeroed */,
+           uint32_t* __restrict__ tile_counter, StatusT* __restrict__ status /* [tiles][256], zeroed */, uint32_t flags,
            const unsigned long long* __restrict__ key_ptrs = nullptr, const unsigned long long* __restrict__ val_ptrs = nullptr) {
     using ST = StatusTraits<StatusT>;
+    using SM = PassSmem<Cfg, kHasValues>;
     constexpr int kBlock = Cfg::kBlock, kIPT = Cfg::kIPT, kTile = Cfg::kTile, kWarps = Cfg::kWarps;
-    constexpr int kMatchBytes = Cfg::kMatchBytes;
+    constexpr int kGroups = 2 * kWarps, kH = SM::kH, kGP = kGroups / kH;      // groups per scan thread
+    static_assert(kIPT % 4 == 0 && 16 * kIPT <= 256, "ranks are packed four to a register (< 256 each)");
+    static_assert(kGroups % kH == 0, "scan threads split the groups evenly");
     extern __shared__ __align__(16) unsigned char smem[];
-    uint2* s_match = reinterpret_cast<uint2*>(smem);                              // [kWarps][256]
-    uint2* s_pairs = reinterpret_cast<uint2*>(smem + kMatchBytes);                // kHasValues
-    uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem + kMatchBytes);           // !kHasValues
-    uint32_t* s_global_off = reinterpret_cast<uint32_t*>(smem + kMatchBytes + PassSmem<Cfg, kHasValues>::kPairBytes);
-    uint32_t* s_scan = s_global_off + kRadix;
+    uint32_t* s_tbl = reinterpret_cast<uint32_t*>(smem);                         // [kGroups][256]
+    uint2* s_pairs = reinterpret_cast<uint2*>(smem + SM::kTblBytes);             // kHasValues
+    uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem + SM::kTblBytes);        // !kHasValues
+    uint32_t* s_global_off = reinterpret_cast<uint32_t*>(smem + SM::kTblBytes + SM::kPairBytes);
+    uint32_t* s_part = s_global_off + kRadix;                                    // [kH][256]
+    uint32_t* s_scan = s_part + kH * kRadix;                                     // [kWarps]
     uint32_t* s_tile_id = s_scan + kWarps;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -182,97 +198,152 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
 #pragma unroll
-        for (int i = 0; i < kMatchBytes / 16 / kBlock; ++i) z[tid + i * kBlock] = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < SM::kTblBytes / 16 / kBlock; ++i) z[tid + i * kBlock] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     const uint32_t tile = *s_tile_id;
     const uint32_t tile_base = tile * (uint32_t)kTile;
     const uint32_t valid = min((uint32_t)kTile, n - tile_base);
 
-    // warp-striped load: consecutive lanes read consecutive keys (one 128-B line per warp request);
-    // item order (round i, lane) is the original order, which the ranking below preserves.
-    const uint32_t warp_first = warp * (32u * kIPT);
+    // Group-major item map: 16-lane group G = 2*warp + lane/16 owns the 16*IPT consecutive keys from G*16*IPT,
+    // item i of lane l16 is key G*16*IPT + 16*i + l16 -- so (round, lane) order inside a group IS memory order,
+    // which is what makes the per-group ranks stable.
+    const uint32_t l16 = lane & 15u;
+    const uint32_t group = 2u * warp + (lane >> 4);
+    const uint32_t item0 = group * (16u * kIPT) + l16;
     uint32_t key[kIPT];
+#ifndef USRT_LAB_SHFL_LOADS
+    // direct form: every load touches two 64-byte segments, one per group (two L1 wavefronts instead of one)
 #pragma unroll
     for (int i = 0; i < kIPT; ++i) {
-        const uint32_t idx = warp_first + (uint32_t)i * 32u + lane;
+        const uint32_t idx = item0 + (uint32_t)i * 16u;
         key[i] = idx < valid ? __ldg(keys_in + tile_base + idx) : 0xFFFFFFFFu;   // tail pads sort last, never stored
     }
-
-    // stable rank of every key among the keys of its warp with the same digit (< 512: two per register)
-    uint32_t rank2[kIPT / 2];
-    const uint32_t lt = lanemask_lt();
-    const uint32_t lane_bit = 1u << lane;
-    uint2* my_match = s_match + warp * kRadix;
-    uint32_t* my_words = reinterpret_cast<uint32_t*>(my_match);
-    // Word d is the 8-byte pair my_match[d] = {mask, count}, with the two halves SWAPPED when bit 4 of
-    // d is set: the 32-bit mask of digit d then lives in bank (2d + ((d >> 4) & 1)) mod 32, so the
-    // atomics (and the count/base lookups, which use the other half) spread over all 32 banks.
+#else
+    // (measured slower, 0.348 vs 0.334 ms per pass at 2^26: the shuffles cost more than the extra load wavefronts)
+    // Warp-striped 128-byte loads over the warp's 32*IPT keys, then one lane-xor-16 shuffle per pair of loads hands
+    // each half-warp the half of the chunk it owns: load i < IPT/2 holds group A's items 2i (lanes 0-15) and 2i+1
+    // (lanes 16-31); load i + IPT/2 holds group B's items 2i and 2i+1 the same way.
+    const bool upper = (lane & 16u) != 0u;
+    const uint32_t warp_first = warp * (32u * kIPT) + lane;
+    auto load_items = [&](const uint32_t* __restrict__ src, uint32_t (&item)[kIPT], uint32_t pad) {
 #pragma unroll
-    for (int i = 0; i < kIPT; ++i) {
-        const uint32_t d = (key[i] >> shift) & 255u;
-        const uint32_t sel = (d >> 4) & 1u;
-        atomicOr(my_words + 2u * d + sel, lane_bit);
-        __syncwarp();
-        const uint2 w = my_match[d];                     // peers of this round + peers of earlier rounds
-        __syncwarp();
-        const uint32_t mask = sel ? w.y : w.x, prior = sel ? w.x : w.y;
-        const uint32_t before = __popc(mask & lt);
-        if (before == 0) {
-            const uint32_t now = prior + __popc(mask);
-            my_match[d] = sel ? make_uint2(now, 0u) : make_uint2(0u, now);
+        for (int i = 0; i < kIPT / 2; ++i) {
+            const uint32_t ia = warp_first + (uint32_t)i * 32u, ib = ia + 16u * kIPT;
+            const uint32_t a = ia < valid ? __ldg(src + tile_base + ia) : pad;
+            const uint32_t b = ib < valid ? __ldg(src + tile_base + ib) : pad;
+            const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, upper ? a : b, 16);
+            item[2 * i] = upper ? got : a;
+            item[2 * i + 1] = upper ? b : got;
         }
-        const uint32_t r = prior + before;
-        if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
-        __syncwarp();
+    };
+    load_items(keys_in, key, 0xFFFFFFFFu);                   // tail pads sort last, never stored
+#endif
+
+    // stable rank of every key among the keys of its group with the same digit (< 256: four per register)
+    uint32_t rank4[kIPT / 4];
+    uint32_t* tbl = s_tbl + group * kRadix;
+    {
+        const uint32_t add = (0x10000u << l16) | 1u, bit = 0x10000u << l16;
+        const uint32_t not_below = 0xFFFFu << l16;             // my own lane and the higher ones of my group
+        uint32_t out_of_order = flags & 1u;
+#pragma unroll
+        for (int i = 0; i < kIPT; ++i) {
+            const uint32_t d = (key[i] >> shift) & 255u;
+            const uint32_t old = atomicAdd(tbl + d, add);
+            __syncwarp();
+            atomicSub(tbl + d, bit);
+#ifndef USRT_LAB_NO_SYNC2
+            __syncwarp();
+#endif
+            out_of_order |= (old >> 16) & not_below;
+            const uint32_t r = old & 0xFFFFu;
+            if ((i & 3) == 0) rank4[i >> 2] = r; else rank4[i >> 2] |= r << ((i & 3) * 8);
+        }
+        if (__any_sync(0xFFFFFFFFu, out_of_order != 0u)) {
+            // Order-independent ranking (never taken on B200 unless forced): start the warp's two tables over.
+            uint32_t* mine = s_tbl + 2u * warp * kRadix;
+#pragma unroll
+            for (int i = 0; i < 2 * kRadix / 32; ++i) mine[lane + 32 * i] = 0u;
+            __syncwarp();
+            const uint32_t below = (1u << l16) - 1u;
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) {
+                const uint32_t d = (key[i] >> shift) & 255u;
+                atomicAdd(tbl + d, add);
+                __syncwarp();
+                const uint32_t now = tbl[d];                    // every peer of this round has added itself
+                __syncwarp();
+                const uint32_t peers = now >> 16, total = now & 0xFFFFu;
+                const uint32_t before = __popc(peers & below);
+                if (before == 0) tbl[d] = total;                // the lowest peer clears the round's lane bits
+                __syncwarp();
+                const uint32_t r = total - __popc(peers) + before;
+                if ((i & 3) == 0) rank4[i >> 2] = r; else rank4[i >> 2] |= r << ((i & 3) * 8);
+            }
+        }
     }
     __syncthreads();
 
     // values are fetched now, so their latency hides behind the scan and the look-back below
     uint32_t val[kHasValues ? kIPT : 1];
     if (kHasValues) {
+#ifndef USRT_LAB_SHFL_LOADS
 #pragma unroll
         for (int i = 0; i < kIPT; ++i) {
-            const uint32_t idx = warp_first + (uint32_t)i * 32u + lane;
+            const uint32_t idx = item0 + (uint32_t)i * 16u;
             val[i] = idx < valid ? __ldg(vals_in + tile_base + idx) : 0u;
         }
+#else
+        load_items(vals_in, reinterpret_cast<uint32_t (&)[kIPT]>(val), 0u);
+#endif
     }
 
-    // thread d (< 256) owns digit d: tile count, exclusive offsets across warps, look-back
-    const uint32_t d = tid;
-    uint32_t* s_words = reinterpret_cast<uint32_t*>(s_match);
-    const uint32_t cnt_half = 1u - ((d >> 4) & 1u);      // which half of word d holds the count
-    uint32_t count = 0, incl = 0, my_tile_start = 0;
-    StatusT* my_status = status + (size_t)tile * kRadix + (d & 255u);
-    if (d < kRadix) {
+    // Scan step: kH threads per digit, each owning kGP consecutive groups. Thread (d, h) sums its groups' counts of
+    // digit d, the kH partial sums meet in s_part, every thread then knows the tile's count of d (published for the
+    // look-back right away) and the counts of the groups before its own.
+    const uint32_t d = tid & 255u, h = tid >> 8;
+    uint32_t cnt[kGP];
+    uint32_t part = 0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) count += s_words[(w * kRadix + d) * 2 + cnt_half];
-        // publish this tile's count of digit d as early as possible
-        ST::store(my_status, (tile == 0 ? ST::kPrefix : ST::kAggregate) | (StatusT)count);
-        incl = count;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= (uint32_t)o) incl += y;
-        }
-        if (lane == 31) s_scan[warp] = incl;
+    for (int j = 0; j < kGP; ++j) { cnt[j] = s_tbl[(h * kGP + j) * kRadix + d]; part += cnt[j]; }
+    if (kH > 1) {
+        s_part[h * kRadix + d] = part;
+        __syncthreads();
     }
+    uint32_t count = 0, groups_before = 0;
+    if (kH > 1) {
+#pragma unroll
+        for (int k = 0; k < kH; ++k) {
+            const uint32_t v = s_part[k * kRadix + d];
+            count += v;
+            groups_before += (k < (int)h) ? v : 0u;
+        }
+    } else {
+        count = part;
+    }
+    StatusT* my_status = status + (size_t)tile * kRadix + d;
+    if (h == 0) ST::store(my_status, (tile == 0 ? ST::kPrefix : ST::kAggregate) | (StatusT)count);
+    // exclusive scan of the 256 digit counts (every h does it for itself: no extra barrier, the values are the same)
+    uint32_t incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    if (lane == 31) s_scan[warp] = incl;
     __syncthreads();
-    if (d < kRadix) {
+    uint32_t tile_start;                                        // first tile-local slot of digit d
+    {
+        const uint32_t w0 = h * (kRadix / 32);                  // first warp of my h
         uint32_t wbase = 0;
 #pragma unroll
-        for (int w = 0; w < kRadix / 32; ++w) wbase += (w < (int)warp) ? s_scan[w] : 0u;
-        const uint32_t tile_start = wbase + incl - count;     // first tile-local slot of digit d
-        // in place: word[w][d].count becomes the first tile slot of warp w's keys of digit d
-        uint32_t running = tile_start;
+        for (int w = 0; w < kRadix / 32; ++w) wbase += (w0 + w < warp) ? s_scan[w0 + w] : 0u;
+        tile_start = wbase + incl - count;
+        // in place: the count of (group, d) becomes the first tile slot of that group's keys of digit d
+        uint32_t running = tile_start + groups_before;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t c = s_words[(w * kRadix + d) * 2 + cnt_half];
-            s_words[(w * kRadix + d) * 2 + cnt_half] = running;
-            running += c;
-        }
-
-        my_tile_start = tile_start;
+        for (int j = 0; j < kGP; ++j) { s_tbl[(h * kGP + j) * kRadix + d] = running; running += cnt[j]; }
     }
     __syncthreads();
 
@@ -280,14 +351,13 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
 #pragma unroll
     for (int i = 0; i < kIPT; ++i) {
         const uint32_t dg = (key[i] >> shift) & 255u;
-        const uint32_t slot = my_words[2u * dg + 1u - ((dg >> 4) & 1u)] + ((rank2[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu);
+        const uint32_t slot = tbl[dg] + ((rank4[i >> 2] >> ((i & 3) * 8)) & 0xFFu);
         if (kHasValues) s_pairs[slot] = make_uint2(key[i], val[i]);
         else s_keys[slot] = key[i];
     }
     // Look-back AFTER staging: the aggregate was published before the scan, so by now the preceding
     // tiles have usually posted their inclusive prefixes and the walk resolves in one round trip.
-    if (d < kRadix) {
-        const uint32_t tile_start = my_tile_start;
+    if (h == 0) {
         // decoupled look-back over the preceding tiles' counts of this digit, four tiles per round
         // trip (the loads are independent; only the accumulation is ordered)
         uint32_t exclusive = 0;
@@ -350,6 +420,10 @@ inline bool wide_status(uint64_t count) {
     static const bool forced = getenv("USRT_FORCE_WIDE_STATUS") != nullptr;   // test hook: 64-bit look-back words at any size
     return forced || count >= (1ull << 30);
 }
+inline uint32_t pass_flags() {
+    static const uint32_t f = getenv("USRT_FORCE_SLOW_RANK") != nullptr ? 1u : 0u;   // test hook: order-independent ranking everywhere
+    return f;
+}
 inline uint64_t status_words_bytes(uint64_t count) { return (uint64_t)num_tiles(count) * kRadix * (wide_status(count) ? 8 : 4); }
 
 template <typename Cfg, typename StatusT, bool kHasValues>
@@ -358,7 +432,7 @@ cudaError_t launch_pass(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, ui
     constexpr int smem = PassSmem<Cfg, kHasValues>::kTotal;
     cudaFuncSetAttribute(k_onesweep<Cfg, StatusT, kHasValues>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     k_onesweep<Cfg, StatusT, kHasValues><<<num_tiles(count), Cfg::kBlock, smem, stream>>>(
-        ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter, static_cast<StatusT*>(status));
+        ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter, static_cast<StatusT*>(status), pass_flags());
     return cudaGetLastError();
 }
 
@@ -498,12 +572,12 @@ cudaError_t partition_scatter(const uint32_t* src_keys, const uint32_t* src_vals
         constexpr int smem = PassSmem<SmallTile, true>::kTotal;
         cudaFuncSetAttribute(k_onesweep<SmallTile, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         k_onesweep<SmallTile, uint32_t, true, true><<<num_tiles(count), SmallTile::kBlock, smem, stream>>>(
-            src_keys, src_vals, nullptr, nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, key_ptrs, val_ptrs);
+            src_keys, src_vals, nullptr, nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, pass_flags(), key_ptrs, val_ptrs);
     } else {
         constexpr int smem = PassSmem<BigTile, true>::kTotal;
         cudaFuncSetAttribute(k_onesweep<BigTile, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         k_onesweep<BigTile, uint32_t, true, true><<<num_tiles(count), BigTile::kBlock, smem, stream>>>(
-            src_keys, src_vals, nullptr, nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, key_ptrs, val_ptrs);
+            src_keys, src_vals, nullptr, nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, pass_flags(), key_ptrs, val_ptrs);
     }
     if (launches) *launches += 1;
     return cudaGetLastError();
