@@ -362,3 +362,58 @@ def test_many_tiny_meshes_and_ragged_ray_counts(usrt, oracle):
         assert _same(ctx.trace_rays(rays), ref.trace_rays(rays)), (trial, n, m)
     assert len(ctx.trace_rays(np.zeros((0, 8), np.float32))) == 0
     ctx.close()
+
+
+# ---- BASELINE configurations at their stated sizes ------------------------------------------------------------------
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _ref_digests(name):
+    """sha256s written by tests/golden/make_ref_golden.py from the reference's own code (oracle/_ref)."""
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_digests.json")))[name]
+
+
+def _check_config(usrt, oracle, tris, cam, w, h, golden):
+    """All six build buffers + the full primary frame: CUDA == oracle (live, byte for byte) == reference-generated digest."""
+    import os
+    n = len(tris)
+    assert _sha(tris) == golden["triangles"], "mesh generator output differs from the one the goldens were made with"
+    ref = oracle.Scene(tris)
+    ctx = usrt.Context(n)
+    ctx.upload_triangles(tris)
+    ctx.rebuild()
+    got = dict(sortedMortonCodes=ctx.download(_lib.BUF_KEYS), sortedTriangleIndices=ctx.download(_lib.BUF_TRIANGLE_INDEX),
+               triangleAABB=ctx.download(_lib.BUF_TRIANGLE_AABB), internalNodes=ctx.download(_lib.BUF_INTERNAL_NODES, n - 1),
+               leafNodes=ctx.download(_lib.BUF_LEAF_NODES), bvhData=ctx.download(_lib.BUF_BVH_DATA, n - 1))
+    want = dict(sortedMortonCodes=ref.sortedMortonCodes, sortedTriangleIndices=ref.sortedTriangleIndices,
+                triangleAABB=ref.triangleAABB, internalNodes=ref.internalNodes[:n - 1], leafNodes=ref.leafNodes,
+                bvhData=ref.bvhData[:n - 1])
+    for k in got:
+        assert _same(got[k], want[k]), k                         # vs the oracle, run here
+        assert _sha(got[k]) == golden[k], k                      # vs the reference's own code (committed digest)
+    assert ctx.count_corrupted_nodes() == (0, 0)
+    frame = ctx.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    want_frame = ref.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], threads=os.cpu_count() or 1)
+    assert _report_ties(frame, want_frame) == (0, 0)
+    assert _same(frame, want_frame)
+    assert _sha(frame) == golden["primary_%dx%d" % (w, h)]
+    assert int((frame["distance"] != oracle.max_float()).sum()) == golden["primary_hit_count"]
+    ctx.close()
+
+
+def test_config0_as_stated_65536_triangles_512x512(usrt, oracle):
+    """BASELINE configs[0]: 65,536-triangle soup, Morton -> sort -> LBVH -> refit -> 512x512 primary rays, every record."""
+    _check_config(usrt, oracle, meshes.scene_c1(), meshes.SCENE_SOUP_CAMERA, 512, 512, _ref_digests("config0_soup_65536"))
+
+
+def test_config1_as_stated_1048576_triangles_1080p(usrt, oracle):
+    """BASELINE configs[1] -- the bench workload -- at full size: 1,048,576 triangles (sphere + height field), full
+    rebuild, 1920x1080 primary rays; all six build buffers and all 2,073,600 hit records."""
+    _check_config(usrt, oracle, meshes.scene_c2(), meshes.SCENE_C2_CAMERA, 1920, 1080, _ref_digests("config1_scene_1048576"))
+
+
+def test_reference_scene_mesh_full_frame(usrt, oracle):
+    _check_config(usrt, oracle, meshes.reference_scene_grid(), meshes.REFERENCE_CAMERA, 480, 270, _ref_digests("refgrid_12800"))
