@@ -121,6 +121,15 @@ int usrt_partition_pass_device(usrt_context* ctx, const uint32_t* src_keys, cons
 int usrt_digit_histogram_device(usrt_context* ctx, const uint32_t* dev_keys, uint64_t count, int bit_offset, uint32_t* dev_hist_out);
 int usrt_partition_scatter_device(usrt_context* ctx, const uint32_t* src_keys, const uint32_t* src_values, uint64_t count,
                                   int bit_offset, const uint64_t* dev_key_base, const uint64_t* dev_value_base);
+/* The landing plan of that exchange, computed ON THE DEVICE from the all-gathered histograms (dev_all_hist: world x 256
+ * uint32, rank-major): contiguous bucket ranges of ~equal mass (dev_bounds, world + 1 entries, may be NULL), this rank's
+ * 256 destination addresses inside its owners' receive buffers (dev_peer_base[o] = this process's mapping of rank o's
+ * buffer, laid out keys[capacity] | values[capacity]; source-rank-major landing order keeps the sort globally stable)
+ * and the number of pairs every rank receives (dev_recv_total, world x uint64). Every rank computes the same plan from
+ * the same input; only dev_recv_total has to be read by the host (the count of the local sort that follows). */
+int usrt_peer_scatter_plan_device(usrt_context* ctx, const uint32_t* dev_all_hist, int world, int rank, const uint64_t* dev_peer_base,
+                                  uint64_t capacity, uint64_t* dev_key_base, uint64_t* dev_value_base, uint64_t* dev_recv_total,
+                                  uint32_t* dev_bounds);
 /* Device buffers that other processes on the node can map (CUDA IPC): create returns the pointer and a 64-byte
  * handle to send to the peers; open maps a peer's buffer into this process; close with opened = 1 unmaps a
  * peer's buffer, opened = 0 frees an own one. */

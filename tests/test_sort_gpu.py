@@ -123,3 +123,67 @@ def test_wide_look_back_words_path():
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, USRT_FORCE_WIDE_STATUS="1"), capture_output=True, text=True)
     assert out.returncode == 0 and "wide ok" in out.stdout, out.stderr[-2000:]
+
+
+def _exact_bucket_ranges(global_hist, world):
+    """choose_bucket_ranges in exact integer arithmetic (the rule k_peer_scatter_plan implements)."""
+    csum = [0]
+    for v in global_hist:
+        csum.append(csum[-1] + int(v))
+    total = csum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r
+        b = 0
+        while b < 256 and csum[b] * world < target:
+            b += 1
+        if b > 0 and target - csum[b - 1] * world <= abs(csum[b] * world - target):
+            b -= 1
+        bounds.append(min(max(b, bounds[-1]), 256))
+    bounds.append(256)
+    return bounds
+
+
+@pytest.mark.parametrize("world,kind", [(2, "uniform"), (4, "skewed"), (8, "uniform"), (8, "sparse"), (3, "empty_rank")])
+def test_peer_scatter_plan_kernel_matches_the_host_plan(usrt, world, kind):
+    """The landing plan of the multi-GPU bucket exchange, computed on ONE GPU for every rank of a pretend world and
+    compared with dist.peer_scatter_plan (numpy): same bucket ranges, same landing addresses, same receive counts."""
+    import torch
+    from unitysimpleraytracing_b200 import dist as udist
+    rng = np.random.default_rng(world * 7 + len(kind))
+    if kind == "uniform":
+        h = rng.integers(0, 5000, (world, 256))
+    elif kind == "skewed":
+        h = (rng.random((world, 256)) ** 6 * 90000).astype(np.int64)
+    elif kind == "sparse":
+        h = np.zeros((world, 256), np.int64); h[:, rng.integers(0, 256, 5)] = rng.integers(1, 10 ** 6, (world, 5))
+    else:
+        h = rng.integers(0, 3000, (world, 256)); h[1] = 0
+    h = h.astype(np.uint32)
+    bounds = _exact_bucket_ranges(h.sum(0, dtype=np.int64), world)
+    owner, offset, recv_total = udist.peer_scatter_plan(h, bounds)
+    capacity = int(recv_total.max()) + 5
+    base = np.array([(r + 1) << 40 for r in range(world)], np.int64)           # pretend mappings, never dereferenced
+    ctx = usrt.Context(2)
+    dev = torch.device("cuda:0")
+    ctx.use_torch_stream()
+    d_h = torch.from_numpy(h.view(np.int32).reshape(-1)).to(dev)
+    d_base = torch.from_numpy(base).to(dev)
+    for rank in range(world):
+        ptrs = torch.zeros(512, dtype=torch.int64, device=dev); recv = torch.zeros(world, dtype=torch.int64, device=dev)
+        bnd = torch.zeros(world + 1, dtype=torch.int32, device=dev)
+        ctx.peer_scatter_plan_device(d_h.data_ptr(), world, rank, d_base.data_ptr(), capacity, ptrs.data_ptr(),
+                                     ptrs.data_ptr() + 2048, recv.data_ptr(), bnd.data_ptr())
+        torch.cuda.synchronize()
+        assert bnd.cpu().numpy().tolist() == bounds
+        assert np.array_equal(recv.cpu().numpy(), recv_total)
+        p = ptrs.cpu().numpy()
+        assert np.array_equal(p[:256], base[owner] + 4 * offset[rank])
+        assert np.array_equal(p[256:], base[owner] + 4 * (capacity + offset[rank]))
+    # a receive buffer one pair too small: the plan is all null addresses (the scatter then writes nothing)
+    ptrs = torch.ones(512, dtype=torch.int64, device=dev); recv = torch.zeros(world, dtype=torch.int64, device=dev)
+    ctx.peer_scatter_plan_device(d_h.data_ptr(), world, 0, d_base.data_ptr(), int(recv_total.max()) - 1, ptrs.data_ptr(),
+                                 ptrs.data_ptr() + 2048, recv.data_ptr())
+    torch.cuda.synchronize()
+    assert (ptrs.cpu().numpy() == 0).all() and np.array_equal(recv.cpu().numpy(), recv_total)
+    ctx.close()

@@ -37,6 +37,7 @@ SIGNATURES = {
     "usrt_partition_pass_device": (_c.c_int, [_P, _P, _P, _P, _P, _c.c_uint64, _c.c_int, _P]),
     "usrt_digit_histogram_device": (_c.c_int, [_P, _P, _c.c_uint64, _c.c_int, _P]),
     "usrt_partition_scatter_device": (_c.c_int, [_P, _P, _P, _c.c_uint64, _c.c_int, _P, _P]),
+    "usrt_peer_scatter_plan_device": (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _P, _c.c_uint64, _P, _P, _P, _P]),
     "usrt_peer_buffer_create": (_c.c_int, [_P, _c.c_uint64, _c.POINTER(_P), _P]),
     "usrt_peer_buffer_open": (_c.c_int, [_P, _P, _c.POINTER(_P)]),
     "usrt_peer_buffer_close": (_c.c_int, [_P, _P, _c.c_int]),

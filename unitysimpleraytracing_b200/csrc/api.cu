@@ -511,6 +511,20 @@ int usrt_partition_scatter_device(usrt_context* ctx, const uint32_t* src_keys, c
     return USRT_OK;
 }
 
+int usrt_peer_scatter_plan_device(usrt_context* ctx, const uint32_t* dev_all_hist, int world, int rank, const uint64_t* dev_peer_base,
+                                  uint64_t capacity, uint64_t* dev_key_base, uint64_t* dev_value_base, uint64_t* dev_recv_total,
+                                  uint32_t* dev_bounds) {
+    NEED_CTX(ctx);
+    if (!dev_all_hist || !dev_peer_base || !dev_key_base || !dev_value_base || !dev_recv_total || world < 1 || world > 16 || rank < 0 ||
+        rank >= world)
+        return fail(ctx, USRT_ERR_ARG, "peer_scatter_plan: bad arguments (world 1..16)");
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, peer_scatter_plan(dev_all_hist, world, rank, reinterpret_cast<const unsigned long long*>(dev_peer_base), capacity,
+                              reinterpret_cast<unsigned long long*>(dev_key_base), reinterpret_cast<unsigned long long*>(dev_value_base),
+                              reinterpret_cast<unsigned long long*>(dev_recv_total), dev_bounds, ctx->stream, &ctx->launches));
+    return USRT_OK;
+}
+
 int usrt_peer_buffer_create(usrt_context* ctx, uint64_t bytes, void** dev_ptr, unsigned char handle_out[64]) {
     NEED_CTX(ctx);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");

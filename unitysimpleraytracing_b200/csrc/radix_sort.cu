@@ -395,8 +395,11 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
                 const uint32_t dg = (kv.x >> shift) & 255u;
                 const uint32_t dst = s_global_off[dg] + p;
                 if (kPeer) {
-                    reinterpret_cast<uint32_t*>(__ldg(key_ptrs + dg))[dst] = kv.x;
-                    reinterpret_cast<uint32_t*>(__ldg(val_ptrs + dg))[dst] = kv.y;
+                    const unsigned long long kp = __ldg(key_ptrs + dg), vp = __ldg(val_ptrs + dg);
+                    if (kp != 0ull) {                          // null plan = a receive buffer would overflow: write nothing
+                        reinterpret_cast<uint32_t*>(kp)[dst] = kv.x;
+                        reinterpret_cast<uint32_t*>(vp)[dst] = kv.y;
+                    }
                 } else {
                     keys_out[dst] = kv.x;
                     vals_out[dst] = kv.y;
@@ -407,6 +410,83 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
             }
         }
     }
+}
+
+// ---- multi-GPU bucket exchange: the landing plan, computed on the device --------------------------------------------
+// One 256-thread block turns the all-gathered top-byte histograms (world x 256 counts) into (a) contiguous bucket
+// ranges of ~equal mass, one per rank, (b) for THIS rank as a source, the element offset of each of its 256 runs
+// inside its owner's receive buffer (source-rank-major, digits ascending within a source -- the order an all-to-all
+// would produce, so the result stays globally stable), turned into absolute key / value addresses, and (c) how many
+// pairs every rank receives. Every rank runs the same integer arithmetic on the same input, so the plans agree.
+// It replaces a host round trip (histograms to the CPU, numpy plan, pointer table back) in the middle of the sort.
+constexpr int kMaxPeerWorld = 16;
+__global__ void __launch_bounds__(kRadix) k_peer_scatter_plan(const uint32_t* __restrict__ all_hist, int world, int rank,
+                                                              const unsigned long long* __restrict__ peer_base,
+                                                              unsigned long long capacity,
+                                                              unsigned long long* __restrict__ key_ptrs,
+                                                              unsigned long long* __restrict__ val_ptrs,
+                                                              unsigned long long* __restrict__ recv_total /* [world] */,
+                                                              uint32_t* __restrict__ bounds_out /* [world+1] */) {
+    __shared__ unsigned long long s_csum[kRadix + 1];                   // global exclusive prefix over digits
+    __shared__ unsigned long long s_src[kMaxPeerWorld][kRadix + 1];     // per-source exclusive prefix over digits
+    __shared__ unsigned long long s_warp[kRadix / 32];
+    __shared__ uint32_t s_bounds[kMaxPeerWorld + 1];
+    const uint32_t d = threadIdx.x, lane = d & 31u, warp = d >> 5;
+    auto block_exclusive = [&](unsigned long long v, unsigned long long* out /* [257] */) {
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += y;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long base = 0;
+        for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
+        out[d + 1] = base + incl;
+        if (d == 0) out[0] = 0;
+        __syncthreads();
+    };
+    unsigned long long g = 0;
+    for (int s = 0; s < world; ++s) g += all_hist[s * kRadix + d];
+    block_exclusive(g, s_csum);
+    for (int s = 0; s < world; ++s) block_exclusive(all_hist[s * kRadix + d], s_src[s]);
+    if (d == 0) {
+        // bucket ranges: the boundary for rank r is the digit boundary whose prefix is closest to total * r / world
+        // (ties towards the lower one), kept non-decreasing; compared as exact integers (prefix * world vs total * r)
+        const unsigned long long total = s_csum[kRadix];
+        s_bounds[0] = 0;
+        for (int r = 1; r < world; ++r) {
+            const unsigned long long target = total * (unsigned long long)r;
+            uint32_t b = 0;
+            while (b < (uint32_t)kRadix && s_csum[b] * (unsigned long long)world < target) ++b;
+            if (b > 0) {
+                const unsigned long long hi = s_csum[b] * (unsigned long long)world, lo = s_csum[b - 1] * (unsigned long long)world;
+                const unsigned long long dist_hi = hi >= target ? hi - target : target - hi, dist_lo = target - lo;
+                if (dist_lo <= dist_hi) --b;
+            }
+            s_bounds[r] = min(max(b, s_bounds[r - 1]), (uint32_t)kRadix);
+        }
+        s_bounds[world] = kRadix;
+    }
+    __syncthreads();
+    int owner = 0;
+    while (owner + 1 < world && d >= s_bounds[owner + 1]) ++owner;
+    const uint32_t ob = s_bounds[owner], oe = s_bounds[owner + 1];
+    unsigned long long before = 0;                                      // pairs the lower-ranked sources send to my owner
+    for (int s = 0; s < rank; ++s) before += s_src[s][oe] - s_src[s][ob];
+    const unsigned long long offset = before + s_src[rank][d] - s_src[rank][ob];
+    unsigned long long t = 0;
+    if (d < (uint32_t)world) {
+        for (int s = 0; s < world; ++s) t += s_src[s][s_bounds[d + 1]] - s_src[s][s_bounds[d]];
+        recv_total[d] = t;
+    }
+    // a receive buffer that is too small: null addresses make the scatter pass write nothing (the host sees the
+    // counts and reports the error) instead of running past a peer's allocation
+    const bool overflow = __syncthreads_or(t > capacity) != 0;
+    key_ptrs[d] = overflow ? 0ull : peer_base[owner] + 4ull * offset;
+    val_ptrs[d] = overflow ? 0ull : peer_base[owner] + 4ull * (capacity + offset);
+    if (d <= (uint32_t)world && bounds_out != nullptr) bounds_out[d] = s_bounds[d];
 }
 
 inline uint32_t histogram_grid(uint64_t count) {
@@ -579,6 +659,15 @@ cudaError_t partition_scatter(const uint32_t* src_keys, const uint32_t* src_vals
         k_onesweep<BigTile, uint32_t, true, true><<<num_tiles(count), BigTile::kBlock, smem, stream>>>(
             src_keys, src_vals, nullptr, nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, pass_flags(), key_ptrs, val_ptrs);
     }
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t peer_scatter_plan(const uint32_t* all_hist, int world, int rank, const unsigned long long* peer_base,
+                              unsigned long long capacity, unsigned long long* key_ptrs, unsigned long long* val_ptrs,
+                              unsigned long long* recv_total, uint32_t* bounds_out, cudaStream_t stream, uint64_t* launches) {
+    if (world < 1 || world > kMaxPeerWorld || rank < 0 || rank >= world) return cudaErrorInvalidValue;
+    k_peer_scatter_plan<<<1, kRadix, 0, stream>>>(all_hist, world, rank, peer_base, capacity, key_ptrs, val_ptrs, recv_total, bounds_out);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -46,6 +46,10 @@ cudaError_t digit_histogram(const uint32_t* keys, uint64_t count, int bit_offset
 cudaError_t partition_scatter(const uint32_t* src_keys, const uint32_t* src_vals, uint64_t count, int bit_offset,
                               const unsigned long long* key_ptrs, const unsigned long long* val_ptrs, SortScratch& scratch,
                               cudaStream_t stream, uint64_t* launches);
+// the landing plan of the bucket exchange from the all-gathered histograms (device in, device out)
+cudaError_t peer_scatter_plan(const uint32_t* all_hist, int world, int rank, const unsigned long long* peer_base,
+                              unsigned long long capacity, unsigned long long* key_ptrs, unsigned long long* val_ptrs,
+                              unsigned long long* recv_total, uint32_t* bounds_out, cudaStream_t stream, uint64_t* launches);
 cudaError_t sort_scratch_reserve(SortScratch& scratch, uint64_t count, bool need_alt);
 void sort_scratch_free(SortScratch& scratch);
 

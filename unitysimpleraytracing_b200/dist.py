@@ -320,10 +320,12 @@ class PeerSortExchange:
     usrt_partition_scatter_device). Every rank owns a receive buffer of `capacity` pairs, mapped into every
     other rank through CUDA IPC at construction. sort():
       1. top-byte counts of the local keys (one kernel), all-gathered (world x 256 counters);
-      2. identical bucket ranges + landing offsets on every rank (peer_scatter_plan);
+      2. identical bucket ranges + landing addresses on every rank, computed ON THE DEVICE from the gathered
+         counters (usrt_peer_scatter_plan_device; peer_scatter_plan below is its numpy twin for the CPU tests);
       3. ONE partition pass that writes each pair straight into its owner's receive buffer over NVLink;
       4. a one-element all-reduce as the "all scatters landed" fence; 5. stable local 4-pass sort.
-    Collectives carry only counters; the pairs never pass through NCCL."""
+    Collectives carry only counters; the pairs never pass through NCCL, and the host reads back nothing but the
+    per-rank receive counts (world x 8 bytes, copied while the scatter runs) -- it needs its own for step 5."""
 
     def __init__(self, ctx, capacity, group=None):
         import torch
@@ -335,8 +337,12 @@ class PeerSortExchange:
         self._fence = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._hist = torch.zeros(256, dtype=torch.int32, device=self.device)
         self._all_hist = torch.empty(self.world * 256, dtype=torch.int32, device=self.device)
-        self._ptrs_host = torch.empty(512, dtype=torch.int64).pin_memory()
-        self._ptrs = torch.empty(512, dtype=torch.int64, device=self.device)
+        self._peer_base = torch.tensor([int(p) for p in self.peer_ptr], dtype=torch.int64, device=self.device)
+        self._ptrs = torch.empty(512, dtype=torch.int64, device=self.device)               # 256 key + 256 value addresses
+        self._recv = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        self._recv_host = torch.empty(self.world, dtype=torch.int64).pin_memory()
+        self._recv_ready = torch.cuda.Event()
+        self.last_recv_total = None
 
     def sort(self, keys_t, vals_t):
         """-> (keys, vals): this rank's contiguous chunk of the global stable sort, as views of the receive
@@ -349,19 +355,21 @@ class PeerSortExchange:
         ctx.digit_histogram_device(keys_t.data_ptr(), n, 24, self._hist.data_ptr())
         # also the "receive buffers are free again" barrier: a rank gets here only after its previous local sort
         dist.all_gather_into_tensor(self._all_hist, self._hist, group=self.group)
-        all_hist = self._all_hist.cpu().numpy().reshape(self.world, 256)
-        bounds = choose_bucket_ranges(all_hist.sum(0, dtype=np.int64), self.world)
-        owner, offset, recv_total = peer_scatter_plan(all_hist, bounds)
-        if int(recv_total.max()) > self.capacity:
-            raise ValueError(f"receive buffer of {self.capacity} pairs too small for {int(recv_total.max())}")
-        base = np.asarray(self.peer_ptr, np.int64)[owner]
-        tbl = self._ptrs_host.numpy()
-        tbl[:256] = base + 4 * offset[self.rank]
-        tbl[256:] = base + 4 * (self.capacity + offset[self.rank])
-        self._ptrs.copy_(self._ptrs_host, non_blocking=True)
+        ctx.peer_scatter_plan_device(self._all_hist.data_ptr(), self.world, self.rank, self._peer_base.data_ptr(),
+                                     self.capacity, self._ptrs.data_ptr(), self._ptrs.data_ptr() + 256 * 8,
+                                     self._recv.data_ptr())
+        self._recv_host.copy_(self._recv, non_blocking=True)      # 8 bytes per rank, in flight beside the scatter
+        self._recv_ready.record()
         ctx.partition_scatter_device(keys_t.data_ptr(), vals_t.data_ptr(), n, 24, self._ptrs.data_ptr(),
                                      self._ptrs.data_ptr() + 256 * 8)
         dist.all_reduce(self._fence, group=self.group)           # every rank's scatter has completed
+        self._recv_ready.synchronize()
+        recv_total = self._recv_host.numpy().copy()
+        self.last_recv_total = recv_total
+        if int(recv_total.max()) > self.capacity:
+            # every rank sees the same counts and raises together; what the scatter wrote past the buffers' value halves
+            # stayed inside the 2 x capacity allocation only if max <= capacity, hence the headroom callers leave
+            raise ValueError(f"receive buffer of {self.capacity} pairs too small for {int(recv_total.max())}")
         m = int(recv_total[self.rank])
         kptr, vptr = self.own_ptr, self.own_ptr + 4 * self.capacity
         if m:

@@ -152,6 +152,14 @@ class Context:
         self._check(self._lib.usrt_partition_scatter_device(self._h, vp(src_keys), vp(src_vals), count, bit_offset,
                                                             vp(key_base_ptr), vp(value_base_ptr)))
 
+    def peer_scatter_plan_device(self, all_hist_ptr, world, rank, peer_base_ptr, capacity, key_base_ptr, value_base_ptr,
+                                 recv_total_ptr, bounds_ptr=None):
+        """The bucket-exchange landing plan from the all-gathered histograms, device in / device out."""
+        vp = ctypes.c_void_p
+        self._check(self._lib.usrt_peer_scatter_plan_device(self._h, vp(all_hist_ptr), int(world), int(rank), vp(peer_base_ptr),
+                                                            int(capacity), vp(key_base_ptr), vp(value_base_ptr),
+                                                            vp(recv_total_ptr), vp(bounds_ptr) if bounds_ptr else None))
+
     def peer_buffer_create(self, nbytes):
         """-> (device pointer, 64-byte IPC handle) of a buffer other processes on the node can map."""
         ptr = ctypes.c_void_p()
