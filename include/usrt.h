@@ -59,8 +59,22 @@ typedef enum usrt_buffer {
     USRT_BUF_BVH_DATA = 4,        /* usrt_aabb[capacity]  internal-node boxes */
     USRT_BUF_LEAF_NODES = 5,      /* usrt_leaf_node[capacity] */
     USRT_BUF_INTERNAL_NODES = 6,  /* usrt_internal_node[capacity] */
-    USRT_BUF_COUNT = 7
+    USRT_BUF_KEYS64 = 7,          /* uint64[capacity]  the keys in key mode USRT_KEYS_MORTON64 (then USRT_BUF_KEYS is void) */
+    USRT_BUF_COUNT = 8
 } usrt_buffer;
+
+/* Key variants, chosen per context with usrt_set_key_mode; every stage entry point keeps its meaning.
+ * Results of modes 1 and 2 differ from the reference's by construction (different keys => different tree); each has an
+ * oracle twin and is bit-exact against it. */
+typedef enum usrt_key_mode {
+    USRT_KEYS_REFERENCE = 0,       /* 30-bit Morton in uint32, made unique by DistributeKeys: the reference, the default */
+    USRT_KEYS_INDEX_TIEBREAK = 1,  /* same codes, NO DistributeKeys: delta() breaks ties between equal codes with the sorted
+                                      position, i.e. works on (code << 32 | index) -- Karras 2012's own rule, instead of the
+                                      reference's "we guarantee that x_code != y_code" (BVH.compute:29). usrt_distribute_keys
+                                      returns USRT_ERR_STATE in this mode. */
+    USRT_KEYS_MORTON64 = 2         /* 63-bit Morton (21 bits per axis) in uint64, 8-pass sort (the reference's sorter is generic
+                                      over uint / ulong keys, ComputeBufferSorter.cs:179-191), 64-bit DistributeKeys, clz64 delta */
+} usrt_key_mode;
 
 typedef struct usrt_context usrt_context;
 
@@ -74,6 +88,8 @@ const char* usrt_version(void);
 int usrt_sync(usrt_context* ctx);
 /* Enqueue on an existing CUDA stream (e.g. torch's current stream) instead of the context's own. */
 int usrt_set_stream(usrt_context* ctx, void* cuda_stream);
+/* Select a key variant (usrt_key_mode). Keys, tree and boxes built in another mode become void (triangles stay). */
+int usrt_set_key_mode(usrt_context* ctx, int mode /* usrt_key_mode */);
 /* World box of NormalizeCentroid, default -125/+125 (MeshBufferContainer.cs:9-15). */
 int usrt_set_world_bounds(usrt_context* ctx, float whole_min, float whole_max);
 /* Per-axis box instead of the cube, and the reference's own TODO ("reduce scene data for finding AABB scene in
@@ -107,6 +123,10 @@ int usrt_sort(usrt_context* ctx);
  * In place. _device: pointers are device memory of this context's GPU, async. _host: synchronous. */
 int usrt_sort_pairs_device(usrt_context* ctx, uint32_t* dev_keys, uint32_t* dev_values, uint64_t count);
 int usrt_sort_pairs_host(usrt_context* ctx, uint32_t* host_keys, uint32_t* host_values, uint64_t count);
+/* ComputeBufferSorter<ulong, uint> (GetRadix is generic over uint / ulong keys, ComputeBufferSorter.cs:179-191): the same
+ * stable ascending LSD sort over 64-bit keys, 8 passes x 8 bits, 32-bit values (may be NULL: keys only). In place. */
+int usrt_sort_pairs64_device(usrt_context* ctx, uint64_t* dev_keys, uint32_t* dev_values, uint64_t count);
+int usrt_sort_pairs64_host(usrt_context* ctx, uint64_t* host_keys, uint32_t* host_values, uint64_t count);
 /* One stable partition pass by an arbitrary 8-bit digit (bit_offset in 0..24) from src to dst; used
  * as the bucket-split step of the multi-GPU sort. histogram_out (device, 256 x uint32) may be NULL. */
 int usrt_partition_pass_device(usrt_context* ctx, const uint32_t* src_keys, const uint32_t* src_values,

@@ -549,6 +549,138 @@ void usrt_oracle_construct_tree(const uint32_t* sortedMortonCodes, uint32_t tria
     }
 }
 
+// ---- SURVEY 8(f)-4 key variants: oracle twins ---------------------------------------------------------------------
+// The reference has neither (its sorter is generic over uint / ulong keys, ComputeBufferSorter.cs:179-191, and
+// _debug/debugShader.compute probes uint64_t, but no 64-bit Morton or tree code ships): these restate the SAME
+// functions above with 64-bit keys, so they are defined here, not pinned by the reference's text.
+
+// Morton3D with 21 bits per axis (the classic 64-bit bit spread), same clamp-and-truncate quantisation as :43-48
+static inline uint64_t ExpandBits64(uint64_t v) {
+    v &= 0x1FFFFFull;
+    v = (v | (v << 32)) & 0x001F00000000FFFFull;
+    v = (v | (v << 16)) & 0x001F0000FF0000FFull;
+    v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+    v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+static inline uint64_t Morton3D64(float x, float y, float z) {
+    x = minf_sel(maxf_sel(x * 2097152.0f, 0.0f), 2097151.0f);
+    y = minf_sel(maxf_sel(y * 2097152.0f, 0.0f), 2097151.0f);
+    z = minf_sel(maxf_sel(z * 2097152.0f, 0.0f), 2097151.0f);
+    return ExpandBits64((uint32_t)x) * 4 + ExpandBits64((uint32_t)y) * 2 + ExpandBits64((uint32_t)z);
+}
+
+void usrt_oracle_morton64(const Triangle* tris, uint32_t n, float whole_min, float whole_max, uint64_t* keys, uint32_t* values,
+                          AABB* aabbs) {
+    for (uint32_t i = 0; i < n; i++) {
+        float centroid[3];
+        GetCentroidAndAABB(tris[i].a, tris[i].b, tris[i].c, centroid, &aabbs[i]);
+        NormalizeCentroid(centroid, whole_min, whole_max);
+        keys[i] = Morton3D64(centroid[0], centroid[1], centroid[2]);
+        values[i] = i;
+    }
+}
+
+// ComputeBufferSorter.Sort() over ulong keys: bitOffset = 0, 8, ..., 56; every pass a stable split by one 8-bit digit
+// (GetRadix :185-188). The block / scan / scatter structure of one pass is restated in usrt_oracle_sort_pass above;
+// its net effect -- a stable counting sort by that digit -- is all a wider key changes, so it is written directly.
+void usrt_oracle_sort64(uint64_t* keys, uint32_t* values, uint64_t count) {
+    std::vector<uint64_t> k2(count);
+    std::vector<uint32_t> v2(count);
+    uint64_t* ka = keys; uint64_t* kb = k2.data();
+    uint32_t* va = values; uint32_t* vb = v2.data();
+    for (int bitOffset = 0; bitOffset < 64; bitOffset += RADIX) {
+        uint64_t start[BUCKET_SIZE + 1] = {0};
+        for (uint64_t i = 0; i < count; ++i) start[((ka[i] >> bitOffset) & (BUCKET_SIZE - 1)) + 1]++;
+        for (uint32_t d = 0; d < BUCKET_SIZE; ++d) start[d + 1] += start[d];
+        for (uint64_t i = 0; i < count; ++i) {
+            const uint64_t dst = start[(ka[i] >> bitOffset) & (BUCKET_SIZE - 1)]++;
+            kb[dst] = ka[i]; vb[dst] = va[i];
+        }
+        std::swap(ka, kb); std::swap(va, vb);
+    }   // 8 passes: the result is back in (keys, values)
+}
+
+void usrt_oracle_stable_sort64(uint64_t* keys, uint32_t* values, uint64_t count) {
+    std::vector<uint64_t> idx(count);
+    for (uint64_t i = 0; i < count; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return keys[a] < keys[b]; });
+    std::vector<uint64_t> k(count); std::vector<uint32_t> v(count);
+    for (uint64_t i = 0; i < count; ++i) { k[i] = keys[idx[i]]; v[i] = values[idx[i]]; }
+    std::memcpy(keys, k.data(), count * 8);
+    std::memcpy(values, v.data(), count * 4);
+}
+
+// MeshBufferContainer.cs:154-169 in unchecked ulong arithmetic
+void usrt_oracle_distribute_keys64(uint64_t* keys, uint32_t trianglesLength) {
+    if (trianglesLength == 0) return;
+    uint64_t newCurrentValue = 0;
+    uint64_t oldCurrentValue = keys[0];
+    keys[0] = newCurrentValue;
+    for (uint32_t i = 1; i < trianglesLength; i++) {
+        newCurrentValue += std::max<uint64_t>(keys[i] - oldCurrentValue, 1ull);
+        oldCurrentValue = keys[i];
+        keys[i] = newCurrentValue;
+    }
+}
+
+// BVH.compute:18-149 over 64-bit keys: clz64 for clz32, everything else word for word. Also the tree of the index
+// tie-break variant: the caller passes (code << 32 | sorted position), Karras 2012's augmented key.
+static inline int clz64(uint64_t v) { return v == 0 ? 64 : __builtin_clzll(v); }
+static inline int delta64(const uint64_t* codes, int x, int y, int numObjects) {
+    if (x >= 0 && x <= numObjects - 1 && y >= 0 && y <= numObjects - 1) return clz64(codes[x] ^ codes[y]);
+    return -1;
+}
+void usrt_oracle_construct_tree64(const uint64_t* codes, uint32_t trianglesCount, InternalNode* internalNodes, LeafNode* leafNodes) {
+    if (trianglesCount < 2) return;
+    const int numObjects = (int)trianglesCount;
+    for (uint32_t threadId = 0; threadId < trianglesCount - 1; ++threadId) {
+        const int idx = (int)threadId;
+        // DetermineRange (:35-52)
+        const int d = sign_i(delta64(codes, idx, idx + 1, numObjects) - delta64(codes, idx, idx - 1, numObjects));
+        const int dmin = delta64(codes, idx, idx - d, numObjects);
+        uint32_t lmax = 2;
+        while (delta64(codes, idx, (int)((uint32_t)idx + lmax * (uint32_t)d), numObjects) > dmin) lmax = lmax * 2;
+        int l = 0;
+        for (uint32_t t = lmax / 2; t >= 1; t /= 2)
+            if (delta64(codes, idx, (int)((uint32_t)idx + ((uint32_t)l + t) * (uint32_t)d), numObjects) > dmin) l += (int)t;
+        const int j = idx + l * d;
+        const int first = std::min(idx, j), last = std::max(idx, j);
+        // FindSplit (:54-92)
+        int split;
+        const uint64_t firstCode = codes[first], lastCode = codes[last];
+        if (firstCode == lastCode) {
+            split = (first + last) >> 1;
+        } else {
+            const int commonPrefix = clz64(firstCode ^ lastCode);
+            split = first;
+            int step = last - first;
+            do {
+                step = (step + 1) >> 1;
+                const int newSplit = split + step;
+                if (newSplit < last && clz64(firstCode ^ codes[newSplit]) > commonPrefix) split = newSplit;
+            } while (step > 1);
+        }
+        // TreeConstructor (:111-147)
+        internalNodes[threadId].index = threadId;
+        if (split == first) {
+            leafNodes[split] = LeafNode{threadId, (uint32_t)split};
+            internalNodes[threadId].leftNode = split; internalNodes[threadId].leftNodeType = LEAF_NODE;
+        } else {
+            internalNodes[split].parent = threadId;
+            internalNodes[threadId].leftNode = split; internalNodes[threadId].leftNodeType = INTERNAL_NODE;
+        }
+        if (split + 1 == last) {
+            leafNodes[split + 1] = LeafNode{threadId, (uint32_t)(split + 1)};
+            internalNodes[threadId].rightNode = split + 1; internalNodes[threadId].rightNodeType = LEAF_NODE;
+        } else {
+            internalNodes[split + 1].parent = threadId;
+            internalNodes[threadId].rightNode = split + 1; internalNodes[threadId].rightNodeType = INTERNAL_NODE;
+        }
+    }
+}
+
 // BVH.compute:172-220 -- leaves climb; the first arrival at a node stops, the second merges. Run
 // serially the outcome is identical to any parallel schedule (min/max are exact and the second
 // arrival always sees both children complete). Counter buffer = BVHConstructor.cs:41 (zeroed).

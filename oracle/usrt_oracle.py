@@ -145,6 +145,65 @@ def construct_bvh(n, sorted_indices, tri_aabb, internal, leaf, capacity=None):
     return bvh
 
 
+# ---- SURVEY 8(f)-4 key variants (defined by the oracle, see usrt_oracle.cpp) ----------------------------------------
+def morton64(tris, whole_min=WHOLE_MIN, whole_max=WHOLE_MAX):
+    n = len(tris)
+    tris = np.ascontiguousarray(tris, dtype=TRIANGLE)
+    keys = np.empty(n, np.uint64); values = np.empty(n, np.uint32); aabbs = np.zeros(n, AABB)
+    lib().usrt_oracle_morton64(_p(tris), ctypes.c_uint32(n), ctypes.c_float(whole_min), ctypes.c_float(whole_max),
+                               _p(keys), _p(values), _p(aabbs))
+    return keys, values, aabbs
+
+
+def sort64(keys, values):
+    k = np.array(keys, np.uint64); v = np.array(values, np.uint32)
+    lib().usrt_oracle_sort64(_p(k), _p(v), ctypes.c_uint64(len(k)))
+    return k, v
+
+
+def stable_sort64(keys, values):
+    k = np.array(keys, np.uint64); v = np.array(values, np.uint32)
+    lib().usrt_oracle_stable_sort64(_p(k), _p(v), ctypes.c_uint64(len(k)))
+    return k, v
+
+
+def distribute_keys64(keys):
+    k = np.array(keys, np.uint64)
+    lib().usrt_oracle_distribute_keys64(_p(k), ctypes.c_uint32(len(k)))
+    return k
+
+
+def construct_tree64(keys64, n):
+    internal = null_internal(n); leaf = null_leaf(n)
+    keys64 = np.ascontiguousarray(keys64, np.uint64)
+    lib().usrt_oracle_construct_tree64(_p(keys64), ctypes.c_uint32(n), _p(internal), _p(leaf))
+    return internal, leaf
+
+
+class VariantScene:
+    """The build with one of the key variants; traversal is the Scene's (it never looks at keys).
+    mode 1: 32-bit Morton codes, NO DistributeKeys, tree on (code << 32 | sorted position).
+    mode 2: 63-bit Morton codes, 8-pass sort, 64-bit DistributeKeys, tree on the distributed 64-bit keys."""
+
+    def __init__(self, tris, mode):
+        self.triangleData = np.ascontiguousarray(tris, TRIANGLE)
+        self.n = n = len(tris)
+        if mode == 1:
+            codes, idx, self.triangleAABB = morton(self.triangleData)
+            self.sortedMortonCodes, self.sortedTriangleIndices = sort(codes, idx)
+            tree_keys = (self.sortedMortonCodes.astype(np.uint64) << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+        elif mode == 2:
+            codes, idx, self.triangleAABB = morton64(self.triangleData)
+            self.sortedMortonRaw, self.sortedTriangleIndices = sort64(codes, idx)
+            self.sortedMortonCodes = tree_keys = distribute_keys64(self.sortedMortonRaw)
+        else:
+            raise ValueError(mode)
+        self.internalNodes, self.leafNodes = construct_tree64(tree_keys, n)
+        self.bvhData = construct_bvh(n, self.sortedTriangleIndices, self.triangleAABB, self.internalNodes, self.leafNodes)
+
+    _scene_args = None
+
+
 class Scene:
     """Everything the build produces, with the reference's buffer names."""
 
@@ -204,6 +263,10 @@ class Scene:
         lib().usrt_oracle_brute_force(_p(self.triangleAABB), _p(self.triangleData), _p(o), ctypes.c_uint32(self.n),
                                       _p(rays), ctypes.c_uint64(len(rays)), _p(out), ctypes.c_int(threads))
         return out
+
+
+for _m in ("_scene_args", "trace_primary", "trace_rays", "visit_order", "brute_force"):
+    setattr(VariantScene, _m, getattr(Scene, _m))
 
 
 def primary_rays(width, height, near, tan_half_fov, cam_to_world):

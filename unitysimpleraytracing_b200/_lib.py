@@ -11,7 +11,9 @@ ERRORS = {-1: "USRT_ERR_ARG", -2: "USRT_ERR_CUDA", -3: "USRT_ERR_STATE", -4: "US
 
 # usrt_buffer
 BUF_KEYS, BUF_TRIANGLE_INDEX, BUF_TRIANGLE_DATA, BUF_TRIANGLE_AABB, BUF_BVH_DATA, BUF_LEAF_NODES, \
-    BUF_INTERNAL_NODES = range(7)
+    BUF_INTERNAL_NODES, BUF_KEYS64 = range(8)
+# usrt_key_mode
+KEYS_REFERENCE, KEYS_INDEX_TIEBREAK, KEYS_MORTON64 = range(3)
 
 _c = ctypes
 _P = _c.c_void_p
@@ -23,6 +25,9 @@ SIGNATURES = {
     "usrt_version": (_c.c_char_p, []),
     "usrt_sync": (_c.c_int, [_P]),
     "usrt_set_stream": (_c.c_int, [_P, _P]),
+    "usrt_set_key_mode": (_c.c_int, [_P, _c.c_int]),
+    "usrt_sort_pairs64_device": (_c.c_int, [_P, _P, _P, _c.c_uint64]),
+    "usrt_sort_pairs64_host": (_c.c_int, [_P, _P, _P, _c.c_uint64]),
     "usrt_set_world_bounds": (_c.c_int, [_P, _c.c_float, _c.c_float]),
     "usrt_capacity": (_c.c_uint32, [_P]),
     "usrt_triangles_length": (_c.c_uint32, [_P]),

@@ -33,6 +33,10 @@ struct usrt_context {
     uint32_t *keys = nullptr, *keys_alt = nullptr;
     uint32_t* keys_primary = nullptr;     // the buffer Morton codes are generated into (fixed for the context)
     uint32_t *tri_index = nullptr, *tri_index_alt = nullptr;
+    // key variants, usrt_set_key_mode: 64-bit key buffers exist only once mode 2 was selected
+    int key_mode = USRT_KEYS_REFERENCE;
+    uint64_t *keys64 = nullptr, *keys64_alt = nullptr, *keys64_primary = nullptr;
+    void* scan_status64 = nullptr;
     usrt_triangle* triangles = nullptr;
     usrt_aabb* tri_aabb = nullptr;
     usrt_aabb* bvh = nullptr;
@@ -121,6 +125,10 @@ int reset_scene_buffers(usrt_context* ctx, size_t lo, size_t hi) {
     CU(ctx, cudaMemsetAsync(ctx->keys_alt + lo, 0xFF, c * 4, ctx->stream));
     CU(ctx, cudaMemsetAsync(ctx->tri_index + lo, 0xFF, c * 4, ctx->stream));
     CU(ctx, cudaMemsetAsync(ctx->tri_index_alt + lo, 0xFF, c * 4, ctx->stream));
+    if (ctx->keys64) {
+        CU(ctx, cudaMemsetAsync(ctx->keys64 + lo, 0xFF, c * 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(ctx->keys64_alt + lo, 0xFF, c * 8, ctx->stream));
+    }
     CU(ctx, cudaMemsetAsync(ctx->leaf + lo, 0xFF, c * sizeof(usrt_leaf_node), ctx->stream));
     CU(ctx, cudaMemsetAsync(ctx->tri_aabb + lo, 0, c * sizeof(usrt_aabb), ctx->stream));
     // internal nodes / node boxes are written for [0, n-1): slot n-1 of the new mesh must be restored too
@@ -156,8 +164,10 @@ int ensure_rays(usrt_context* ctx, uint64_t count) {
 }
 
 int do_morton(usrt_context* ctx) {
-    CU(ctx, launch_morton(ctx->triangles, ctx->n, ctx->whole, ctx->keys, ctx->tri_index,
-                          ctx->tri_aabb, ctx->stream));
+    if (ctx->key_mode == USRT_KEYS_MORTON64)
+        CU(ctx, launch_morton64(ctx->triangles, ctx->n, ctx->whole, ctx->keys64, ctx->tri_index, ctx->tri_aabb, ctx->stream));
+    else
+        CU(ctx, launch_morton(ctx->triangles, ctx->n, ctx->whole, ctx->keys, ctx->tri_index, ctx->tri_aabb, ctx->stream));
     ctx->launches += 1;
     ctx->stage = ST_TRIS | ST_MORTON;
     return USRT_OK;
@@ -165,6 +175,12 @@ int do_morton(usrt_context* ctx) {
 
 int do_sort(usrt_context* ctx) {
     ctx->sort_ev_valid = false;
+    if (ctx->key_mode == USRT_KEYS_MORTON64) {
+        CU(ctx, sort_pairs64(ctx->keys64, ctx->tri_index, ctx->keys64_alt, ctx->tri_index_alt, ctx->n, ctx->sort, ctx->stream,
+                             &ctx->launches));
+        ctx->stage |= ST_SORTED;
+        return USRT_OK;
+    }
     CU(ctx, sort_pairs(ctx->keys, ctx->tri_index, ctx->keys_alt, ctx->tri_index_alt, ctx->n, ctx->sort, ctx->stream,
                        &ctx->launches, ctx->timing ? ctx->sort_ev : nullptr));
     ctx->sort_ev_valid = ctx->timing && ctx->n > 0;
@@ -174,15 +190,21 @@ int do_sort(usrt_context* ctx) {
 
 int do_distribute(usrt_context* ctx) {
     int l = 0;
-    CU(ctx, launch_distribute_keys(ctx->keys, ctx->keys_alt, ctx->n, ctx->scan_status, ctx->stream, &l));
+    if (ctx->key_mode == USRT_KEYS_MORTON64) {
+        CU(ctx, launch_distribute_keys64(ctx->keys64, ctx->keys64_alt, ctx->n, ctx->scan_status64, ctx->stream, &l));
+        std::swap(ctx->keys64, ctx->keys64_alt);
+    } else {
+        CU(ctx, launch_distribute_keys(ctx->keys, ctx->keys_alt, ctx->n, ctx->scan_status, ctx->stream, &l));
+        std::swap(ctx->keys, ctx->keys_alt);    // the distributed keys ARE the keys buffer from here on
+    }
     ctx->launches += l;
-    std::swap(ctx->keys, ctx->keys_alt);        // the distributed keys ARE the keys buffer from here on
     ctx->stage |= ST_DISTRIBUTED;
     return USRT_OK;
 }
 
 int do_tree(usrt_context* ctx) {
-    CU(ctx, launch_construct_tree(ctx->keys, ctx->n, ctx->internal, ctx->leaf, ctx->up_internal, ctx->up_leaf, ctx->stream));
+    const void* keys = ctx->key_mode == USRT_KEYS_MORTON64 ? static_cast<const void*>(ctx->keys64) : static_cast<const void*>(ctx->keys);
+    CU(ctx, launch_construct_tree(keys, ctx->key_mode, ctx->n, ctx->internal, ctx->leaf, ctx->up_internal, ctx->up_leaf, ctx->stream));
     ctx->launches += 1;
     ctx->stage |= ST_TREE;
     return USRT_OK;
@@ -262,7 +284,7 @@ int usrt_destroy(usrt_context* ctx) {
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     void* ptrs[] = {ctx->keys, ctx->keys_alt, ctx->tri_index, ctx->tri_index_alt, ctx->triangles, ctx->tri_aabb,
                     ctx->bvh, ctx->leaf, ctx->internal, ctx->slots, ctx->up_internal, ctx->up_leaf, ctx->packed_nodes, ctx->packed_tris,
-                    ctx->scan_status, ctx->small, ctx->scene_box, ctx->hits, ctx->rays, ctx->texture, ctx->shaded};
+                    ctx->scan_status, ctx->scan_status64, ctx->keys64, ctx->keys64_alt, ctx->small, ctx->scene_box, ctx->hits, ctx->rays, ctx->texture, ctx->shaded};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     sort_scratch_free(ctx->sort);
@@ -559,10 +581,75 @@ int usrt_peer_buffer_close(usrt_context* ctx, void* dev_ptr, int opened) {
     return USRT_OK;
 }
 
+int usrt_set_key_mode(usrt_context* ctx, int mode) {
+    NEED_CTX(ctx);
+    if (mode != USRT_KEYS_REFERENCE && mode != USRT_KEYS_INDEX_TIEBREAK && mode != USRT_KEYS_MORTON64)
+        return fail(ctx, USRT_ERR_ARG, "set_key_mode: unknown mode %d", mode);
+    if (int r = bind_device(ctx)) return r;
+    if (mode == USRT_KEYS_MORTON64 && !ctx->keys64) {
+        const size_t c = ctx->capacity;
+        CU(ctx, cudaMalloc(&ctx->keys64, c * 8));
+        CU(ctx, cudaMalloc(&ctx->keys64_alt, c * 8));
+        CU(ctx, cudaMalloc(&ctx->scan_status64, distribute_status_bytes64(ctx->capacity)));
+        ctx->keys64_primary = ctx->keys64;
+        CU(ctx, cudaMemsetAsync(ctx->keys64, 0xFF, c * 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(ctx->keys64_alt, 0xFF, c * 8, ctx->stream));
+        CU(ctx, sort_scratch_reserve64(ctx->sort, ctx->capacity, false));
+    }
+    if (mode != ctx->key_mode) {
+        ctx->key_mode = mode;
+        ctx->stage &= ST_TRIS;                            // keys, tree and boxes of the other mode are void
+        if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+    }
+    return USRT_OK;
+}
+
+int usrt_sort_pairs64_device(usrt_context* ctx, uint64_t* dev_keys, uint32_t* dev_values, uint64_t count) {
+    NEED_CTX(ctx);
+    if (count && !dev_keys) return fail(ctx, USRT_ERR_ARG, "sort_pairs64: null keys");
+    if (count >= (1ull << 32)) return fail(ctx, USRT_ERR_ARG, "sort_pairs64: count must be < 2^32");
+    if (int r = bind_device(ctx)) return r;
+    CU(ctx, sort_scratch_reserve64(ctx->sort, std::max<uint64_t>(count, 1), true));
+    ctx->sort_ev_valid = false;
+    CU(ctx, sort_pairs64(dev_keys, dev_values, ctx->sort.keys64_alt, dev_values ? ctx->sort.vals64_alt : nullptr, count, ctx->sort,
+                         ctx->stream, &ctx->launches));
+    return USRT_OK;
+}
+
+int usrt_sort_pairs64_host(usrt_context* ctx, uint64_t* host_keys, uint32_t* host_values, uint64_t count) {
+    NEED_CTX(ctx);
+    if (count == 0) return USRT_OK;
+    if (!host_keys) return fail(ctx, USRT_ERR_ARG, "sort_pairs64_host: null keys");
+    if (count >= (1ull << 32)) return fail(ctx, USRT_ERR_ARG, "sort_pairs64: count must be < 2^32");
+    if (int r = bind_device(ctx)) return r;
+    uint64_t* dk = nullptr;
+    uint32_t* dv = nullptr;
+    CU(ctx, cudaMalloc(&dk, count * 8));
+    if (host_values) {
+        cudaError_t e = cudaMalloc(&dv, count * 4);
+        if (e != cudaSuccess) { cudaFree(dk); return fail(ctx, USRT_ERR_NOMEM, "sort_pairs64_host: %s", cudaGetErrorString(e)); }
+    }
+    auto run = [&]() -> int {
+        CU(ctx, cudaMemcpyAsync(dk, host_keys, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (dv) CU(ctx, cudaMemcpyAsync(dv, host_values, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (int r = usrt_sort_pairs64_device(ctx, dk, dv, count)) return r;
+        CU(ctx, cudaMemcpyAsync(host_keys, dk, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dv) CU(ctx, cudaMemcpyAsync(host_values, dv, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return USRT_OK;
+    };
+    const int rc = run();
+    cudaFree(dk);
+    if (dv) cudaFree(dv);
+    return rc;
+}
+
 int usrt_distribute_keys(usrt_context* ctx) {
     NEED_CTX(ctx);
     if (!(ctx->stage & ST_SORTED)) return fail(ctx, USRT_ERR_STATE, "distribute_keys: keys not sorted (call usrt_sort)");
     if (ctx->stage & ST_DISTRIBUTED) return fail(ctx, USRT_ERR_STATE, "distribute_keys: already applied to these keys");
+    if (ctx->key_mode == USRT_KEYS_INDEX_TIEBREAK)
+        return fail(ctx, USRT_ERR_STATE, "distribute_keys: key mode USRT_KEYS_INDEX_TIEBREAK builds the tree on the raw sorted codes");
     if (int r = bind_device(ctx)) return r;
     return do_distribute(ctx);
 }
@@ -591,7 +678,8 @@ int enqueue_rebuild(usrt_context* ctx, bool timed) {
     if (timed) CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (int r = do_sort(ctx)) return r;
     if (timed) CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    if (int r = do_distribute(ctx)) return r;
+    if (ctx->key_mode != USRT_KEYS_INDEX_TIEBREAK)
+        if (int r = do_distribute(ctx)) return r;
     if (timed) CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     if (int r = do_tree(ctx)) return r;
     if (timed) CU(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -617,6 +705,11 @@ int usrt_rebuild(usrt_context* ctx) {
     // DistributeKeys leaves keys/keys_alt swapped; start every rebuild from the same orientation so the
     // launch sequence (and therefore a captured graph) is identical from one rebuild to the next.
     if (ctx->keys != ctx->keys_primary) std::swap(ctx->keys, ctx->keys_alt);
+    if (ctx->keys64 && ctx->keys64 != ctx->keys64_primary) std::swap(ctx->keys64, ctx->keys64_alt);
+    if (ctx->key_mode != USRT_KEYS_REFERENCE) {          // the variants are enqueued launch by launch (no graph, no stage events)
+        if (int r = enqueue_rebuild(ctx, false)) return r;
+        return USRT_OK;
+    }
 
     if (ctx->timing || !ctx->use_graph) {            // per-stage events are recorded between launches: no graph
         if (int r = enqueue_rebuild(ctx, ctx->timing)) return r;
@@ -938,7 +1031,12 @@ int usrt_hits_device(usrt_context* ctx, void** dev_ptr, uint64_t* count) {
 
 static int buffer_info(usrt_context* ctx, int buffer, void** ptr, size_t* elem) {
     switch (buffer) {
-        case USRT_BUF_KEYS: *ptr = ctx->keys; *elem = 4; return USRT_OK;
+        case USRT_BUF_KEYS:
+            if (ctx->key_mode == USRT_KEYS_MORTON64) return fail(ctx, USRT_ERR_STATE, "key mode USRT_KEYS_MORTON64: the keys are USRT_BUF_KEYS64");
+            *ptr = ctx->keys; *elem = 4; return USRT_OK;
+        case USRT_BUF_KEYS64:
+            if (ctx->key_mode != USRT_KEYS_MORTON64) return fail(ctx, USRT_ERR_STATE, "USRT_BUF_KEYS64 exists in key mode USRT_KEYS_MORTON64 only");
+            *ptr = ctx->keys64; *elem = 8; return USRT_OK;
         case USRT_BUF_TRIANGLE_INDEX: *ptr = ctx->tri_index; *elem = 4; return USRT_OK;
         case USRT_BUF_TRIANGLE_DATA: *ptr = ctx->triangles; *elem = sizeof(usrt_triangle); return USRT_OK;
         case USRT_BUF_TRIANGLE_AABB: *ptr = ctx->tri_aabb; *elem = sizeof(usrt_aabb); return USRT_OK;

@@ -135,15 +135,96 @@ __global__ void __launch_bounds__(kScanBlock) k_distribute_keys(const uint32_t* 
     }
 }
 
+// K3 on 64-bit keys: the same recurrence in wrapping uint64. Not on the headline path, so the scan is
+// the plain three-step form: per-tile sums, one block scanning the tile sums, per-tile apply. One key per thread.
+constexpr int kDk64Tile = 1024;
+
+__device__ __forceinline__ uint64_t dk64_increment(const uint64_t* __restrict__ src, uint32_t i, uint32_t n) {
+    if (i == 0 || i >= n) return 0ull;
+    const uint64_t d = __ldg(src + i) - __ldg(src + i - 1);             // wrapping, like C# unchecked ulong
+    return d > 1ull ? d : 1ull;                                          // Math.Max(ulong, 1)
+}
+
+// inclusive scan over the block's 1024 threads; *total = the block's sum
+__device__ __forceinline__ uint64_t block_inclusive_u64(uint64_t v, uint64_t* s_warp /* [32] */, uint64_t* total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint64_t base = 0, sum = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; ++w) { const uint64_t t = s_warp[w]; if (w < warp) base += t; sum += t; }
+    __syncthreads();
+    *total = sum;
+    return base + incl;
+}
+
+__global__ void __launch_bounds__(kDk64Tile) k_dk64_tile_sums(const uint64_t* __restrict__ src, uint32_t n, uint64_t* __restrict__ sums) {
+    __shared__ uint64_t s_warp[32];
+    uint64_t total;
+    block_inclusive_u64(dk64_increment(src, blockIdx.x * kDk64Tile + threadIdx.x, n), s_warp, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kDk64Tile) k_dk64_scan_sums(uint64_t* __restrict__ sums, uint32_t tiles) {
+    __shared__ uint64_t s_warp[32];
+    uint64_t carry = 0;
+    for (uint32_t base = 0; base < tiles; base += kDk64Tile) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = i < tiles ? sums[i] : 0ull;
+        uint64_t total;
+        const uint64_t incl = block_inclusive_u64(v, s_warp, &total);
+        if (i < tiles) sums[i] = carry + incl - v;                       // exclusive
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(kDk64Tile) k_dk64_apply(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint32_t n,
+                                                          const uint64_t* __restrict__ sums) {
+    __shared__ uint64_t s_warp[32];
+    const uint32_t i = blockIdx.x * kDk64Tile + threadIdx.x;
+    uint64_t total;
+    const uint64_t incl = block_inclusive_u64(dk64_increment(src, i, n), s_warp, &total);
+    if (i < n) dst[i] = sums[blockIdx.x] + incl;
+}
+
 // =================================================================================================
 // K4 -- Karras LBVH topology, one thread per internal node
 // =================================================================================================
-struct KeyView {
+// Key views. The reference builds the tree on 32-bit keys that DistributeKeys made unique (Keys32). Two opt-in
+// variants reuse the same kernel: Keys32Tie skips DistributeKeys and breaks ties between equal Morton
+// codes with the sorted position, i.e. works on the 64-bit key (code << 32 | index) as Karras 2012 proposes; Keys64
+// reads 64-bit (63-bit Morton) keys made unique by the 64-bit DistributeKeys.
+struct Keys32 {
+    typedef uint32_t KeyT;
     const uint32_t* __restrict__ codes;
+    __device__ __forceinline__ KeyT key(int i) const { return __ldg(codes + i); }
+    // BVH.compute:18-21: clz32 = 31 - firstbithigh == __clz, 32 for 0
+    static __device__ __forceinline__ int clz(KeyT x) { return __clz((int)x); }
+};
+struct Keys32Tie {
+    typedef uint64_t KeyT;
+    const uint32_t* __restrict__ codes;
+    __device__ __forceinline__ KeyT key(int i) const { return ((uint64_t)__ldg(codes + i) << 32) | (uint32_t)i; }
+    static __device__ __forceinline__ int clz(KeyT x) { return __clzll((long long)x); }
+};
+struct Keys64 {
+    typedef uint64_t KeyT;
+    const uint64_t* __restrict__ codes;
+    __device__ __forceinline__ KeyT key(int i) const { return __ldg(codes + i); }
+    static __device__ __forceinline__ int clz(KeyT x) { return __clzll((long long)x); }
+};
+
+template <typename View> struct KeyView {
+    View v;
     int n;
-    // BVH.compute:23-33. clz32 (:18-21) == __clz for the non-zero XOR DistributeKeys guarantees; 32 for 0.
+    // BVH.compute:23-33
     __device__ __forceinline__ int delta(int x, int y) const {
-        if (x >= 0 && x <= n - 1 && y >= 0 && y <= n - 1) return __clz((int)(__ldg(codes + x) ^ __ldg(codes + y)));
+        if (x >= 0 && x <= n - 1 && y >= 0 && y <= n - 1) return View::clz(v.key(x) ^ v.key(y));
         return -1;
     }
 };
@@ -154,14 +235,16 @@ struct KeyView {
 constexpr int kRefitBlock = 128;                 // leaves per K5 CTA
 constexpr uint32_t kUpRight = 1u << 30, kUpLocal = 1u << 31, kUpParentMask = (1u << 30) - 1;
 
-__global__ void __launch_bounds__(256) k_construct_tree(const uint32_t* __restrict__ codes, uint32_t n,
+template <typename View>
+__global__ void __launch_bounds__(256) k_construct_tree(View view, uint32_t n,
                                                         usrt_internal_node* __restrict__ internal,
                                                         usrt_leaf_node* __restrict__ leaf,
                                                         uint32_t* __restrict__ up_internal,
                                                         uint32_t* __restrict__ up_leaf) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;                                            // BVH.compute:101
-    const KeyView kv{codes, (int)n};
+    const KeyView<View> kv{view, (int)n};
+    typedef typename View::KeyT KeyT;
     const int idx = (int)i;
 
     // DetermineRange (BVH.compute:35-52); uint*int products wrap in 32 bits as in HLSL
@@ -179,20 +262,18 @@ __global__ void __launch_bounds__(256) k_construct_tree(const uint32_t* __restri
     // FindSplit (BVH.compute:54-92)
     int split;
     {
-        const uint32_t first_code = __ldg(codes + first), last_code = __ldg(codes + last);
+        const KeyT first_code = view.key(first), last_code = view.key(last);
         if (first_code == last_code) {
             split = (first + last) >> 1;
         } else {
-            const int common = __clz((int)(first_code ^ last_code));
+            const int common = View::clz(first_code ^ last_code);
             split = first;
             int step = last - first;
             do {
                 step = (step + 1) >> 1;
                 const int cand = split + step;
                 if (cand < last) {
-                    const uint32_t c = __ldg(codes + cand);
-                    const uint32_t x = first_code ^ c;
-                    const int prefix = x ? __clz((int)x) : 32;
+                    const int prefix = View::clz(first_code ^ view.key(cand));      // all bits for equal keys
                     if (prefix > common) split = cand;
                 }
             } while (step > 1);
@@ -503,10 +584,28 @@ cudaError_t launch_distribute_keys(const uint32_t* src, uint32_t* dst, uint32_t 
     return cudaGetLastError();
 }
 
-cudaError_t launch_construct_tree(const uint32_t* keys, uint32_t n, usrt_internal_node* internal,
+cudaError_t launch_distribute_keys64(const uint64_t* src, uint64_t* dst, uint32_t n, void* scan_status, cudaStream_t stream,
+                                     int* launches) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t tiles = (n + kDk64Tile - 1) / kDk64Tile;
+    uint64_t* sums = static_cast<uint64_t*>(scan_status);               // >= tiles x 8 bytes (distribute_status_bytes64)
+    k_dk64_tile_sums<<<tiles, kDk64Tile, 0, stream>>>(src, n, sums);
+    k_dk64_scan_sums<<<1, kDk64Tile, 0, stream>>>(sums, tiles);
+    k_dk64_apply<<<tiles, kDk64Tile, 0, stream>>>(src, dst, n, sums);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
+uint64_t distribute_status_bytes64(uint32_t n) { return ((uint64_t)(n + kDk64Tile - 1) / kDk64Tile) * 8; }
+
+cudaError_t launch_construct_tree(const void* keys, int key_mode, uint32_t n, usrt_internal_node* internal,
                                   usrt_leaf_node* leaf, uint32_t* up_internal, uint32_t* up_leaf, cudaStream_t stream) {
-    const uint32_t threads = n - 1;
-    k_construct_tree<<<(threads + 255) / 256, 256, 0, stream>>>(keys, n, internal, leaf, up_internal, up_leaf);
+    const uint32_t threads = n - 1, grid = (threads + 255) / 256;
+    if (key_mode == 2)
+        k_construct_tree<<<grid, 256, 0, stream>>>(Keys64{static_cast<const uint64_t*>(keys)}, n, internal, leaf, up_internal, up_leaf);
+    else if (key_mode == 1)
+        k_construct_tree<<<grid, 256, 0, stream>>>(Keys32Tie{static_cast<const uint32_t*>(keys)}, n, internal, leaf, up_internal, up_leaf);
+    else
+        k_construct_tree<<<grid, 256, 0, stream>>>(Keys32{static_cast<const uint32_t*>(keys)}, n, internal, leaf, up_internal, up_leaf);
     return cudaGetLastError();
 }
 

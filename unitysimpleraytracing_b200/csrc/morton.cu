@@ -29,8 +29,25 @@ __device__ __forceinline__ uint32_t quantise(float x) {          // MeshBufferCo
     return (uint32_t)x;                                           // truncation, like C# (uint)float
 }
 
+// 64-bit variant (the reference's sorter is generic over uint / ulong keys but ships no 64-bit Morton
+// function, so this is defined by analogy and restated in the oracle): 21 bits per axis, the classic 64-bit spread.
+__device__ __forceinline__ uint64_t expand_bits64(uint64_t v) {
+    v &= 0x1FFFFFull;
+    v = (v | (v << 32)) & 0x001F00000000FFFFull;
+    v = (v | (v << 16)) & 0x001F0000FF0000FFull;
+    v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+    v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+__device__ __forceinline__ uint32_t quantise21(float x) {
+    x = sel_min(sel_max(__fmul_rn(x, 2097152.0f), 0.0f), 2097151.0f);
+    return (uint32_t)x;
+}
+
+template <bool kWide>
 __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ tris, uint32_t n, WorldBox whole,
-                                                uint32_t* __restrict__ keys,
+                                                uint32_t* __restrict__ keys, uint64_t* __restrict__ keys64,
                                                 uint32_t* __restrict__ values, float4* __restrict__ aabbs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -55,9 +72,11 @@ __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ tris,
     cz = __fdiv_rn(__fsub_rn(cz, whole.min[2]), __fsub_rn(whole.max[2], whole.min[2]));
 
     // Morton3D (:41-50)
-    const uint32_t key = expand_bits(quantise(cx)) * 4 + expand_bits(quantise(cy)) * 2 + expand_bits(quantise(cz));
-
-    keys[i] = key;
+    if (kWide) {
+        keys64[i] = expand_bits64(quantise21(cx)) * 4 + expand_bits64(quantise21(cy)) * 2 + expand_bits64(quantise21(cz));
+    } else {
+        keys[i] = expand_bits(quantise(cx)) * 4 + expand_bits(quantise(cy)) * 2 + expand_bits(quantise(cz));
+    }
     values[i] = i;                                                 // :132
     aabbs[(size_t)i * 2 + 0] = make_float4(mnx, mny, mnz, 0.0f);   // pads are C# default(0)
     aabbs[(size_t)i * 2 + 1] = make_float4(mxx, mxy, mxz, 0.0f);
@@ -112,8 +131,16 @@ cudaError_t launch_morton(const usrt_triangle* tris, uint32_t n, const WorldBox&
     if (n == 0) return cudaSuccess;
     const uint32_t block = 256;
     const uint32_t grid = (n + block - 1) / block;
-    k_morton<<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(tris), n, whole, keys, values,
-                                         reinterpret_cast<float4*>(aabbs));
+    k_morton<false><<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(tris), n, whole, keys, nullptr, values,
+                                                reinterpret_cast<float4*>(aabbs));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_morton64(const usrt_triangle* tris, uint32_t n, const WorldBox& whole, uint64_t* keys, uint32_t* values,
+                            usrt_aabb* aabbs, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_morton<true><<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float4*>(tris), n, whole, nullptr, keys, values,
+                                                        reinterpret_cast<float4*>(aabbs));
     return cudaGetLastError();
 }
 

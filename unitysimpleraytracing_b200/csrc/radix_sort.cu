@@ -117,6 +117,31 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_histogram(const uint32_t* _
     if (sum) atomicAdd(&hist[tid], sum);
 }
 
+// 64-bit keys (ComputeBufferSorter<ulong, uint>): the same four-digit histogram over ONE 32-bit half of every key,
+// launched once per half (the [pass][digit][lane] counters of four digits already fill 128 KB of shared memory).
+__global__ void __launch_bounds__(kHistThreads, 1) k_histogram64(const uint2* __restrict__ keys /* {low, high} */, uint64_t n,
+                                                                 int half, uint32_t* __restrict__ hist /* [4][256], zeroed */) {
+    extern __shared__ uint32_t s_cnt[];                          // [4][256][32]
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    for (int i = tid; i < kSortPasses * kRadix * 32; i += kHistThreads) s_cnt[i] = 0;
+    __syncthreads();
+    uint32_t* col = s_cnt + lane;
+    const uint64_t gstride = (uint64_t)gridDim.x * kHistThreads;
+    for (uint64_t i = (uint64_t)blockIdx.x * kHistThreads + tid; i < n; i += gstride) {
+        const uint2 q = __ldg(keys + i);
+        const uint32_t k = half ? q.y : q.x;
+        atomicAdd(col + ((0 * kRadix + (k & 255u)) << 5), 1u);
+        atomicAdd(col + ((1 * kRadix + ((k >> 8) & 255u)) << 5), 1u);
+        atomicAdd(col + ((2 * kRadix + ((k >> 16) & 255u)) << 5), 1u);
+        atomicAdd(col + ((3 * kRadix + (k >> 24)) << 5), 1u);
+    }
+    __syncthreads();
+    uint32_t sum = 0;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) sum += s_cnt[(tid << 5) + ((l + lane) & 31u)];
+    if (sum) atomicAdd(&hist[tid], sum);
+}
+
 // exclusive scan of each pass's 256 counts -> first output position of every digit (in place).
 // optional copy of the raw counts of one pass (for the multi-GPU bucket split).
 __global__ void __launch_bounds__(kSortPasses * kRadix) k_scan_histogram(uint32_t* __restrict__ hist,
@@ -159,9 +184,9 @@ __global__ void __launch_bounds__(kSortPasses * kRadix) k_scan_histogram(uint32_
 // warp sync, rank = count - popc(mask) + popc(mask below me)). Each lane then takes its bit out again with a second
 // atomic (no return value). Cost per round of 32 keys: 5.6 SM-cycles against 12.4 for round 1's 64-bit
 // {mask,count} words (atomicOr + 64-bit read + leader write-back) and 25 / 60 for ballot / match.any matching.
-template <typename Cfg, bool kHasValues> struct PassSmem {
+template <typename Cfg, bool kHasValues, int kKeyBytes = 4> struct PassSmem {
     static constexpr int kTblBytes = 2 * Cfg::kWarps * kRadix * 4;
-    static constexpr int kPairBytes = Cfg::kTile * (kHasValues ? 8 : 4);
+    static constexpr int kPairBytes = Cfg::kTile * (kKeyBytes + (kHasValues ? 4 : 0));
     static constexpr int kH = Cfg::kBlock / kRadix;                      // threads per digit in the scan step
     static constexpr int kTotal = kTblBytes + kPairBytes + kRadix * 4 + kH * kRadix * 4 + Cfg::kWarps * 4 + 16;
 };
@@ -170,22 +195,27 @@ template <typename Cfg, bool kHasValues> struct PassSmem {
 // (key_ptrs[d] / val_ptrs[d], this rank's slice of the receive buffer of the GPU that owns bucket d, mapped
 // through CUDA IPC): the stable scatter of the pass IS the all-to-all, written straight over NVLink.
 // flags bit 0: test hook, every warp takes the order-independent ranking path.
-template <typename Cfg, typename StatusT, bool kHasValues, bool kPeer = false>
+// KeyT = uint32_t (the reference's ComputeBufferSorter<uint,uint>) or uint64_t (its GetRadix is generic over uint /
+// ulong, ComputeBufferSorter.cs:179-191): 64-bit keys run 8 passes and stage keys and values in separate arrays.
+template <typename Cfg, typename StatusT, bool kHasValues, bool kPeer = false, typename KeyT = uint32_t>
 __global__ void __launch_bounds__(Cfg::kBlock, Cfg::kCtasPerSM)
-k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ digit_base /* [256] */,
            uint32_t* __restrict__ tile_counter, StatusT* __restrict__ status /* [tiles][256], zeroed */, uint32_t flags,
            const unsigned long long* __restrict__ key_ptrs = nullptr, const unsigned long long* __restrict__ val_ptrs = nullptr) {
     using ST = StatusTraits<StatusT>;
-    using SM = PassSmem<Cfg, kHasValues>;
+    using SM = PassSmem<Cfg, kHasValues, (int)sizeof(KeyT)>;
+    constexpr bool kWide = sizeof(KeyT) == 8;
+    static_assert(!(kWide && kPeer), "the multi-GPU bucket exchange is built for 32-bit keys");
     constexpr int kBlock = Cfg::kBlock, kIPT = Cfg::kIPT, kTile = Cfg::kTile, kWarps = Cfg::kWarps;
     constexpr int kGroups = 2 * kWarps, kH = SM::kH, kGP = kGroups / kH;      // groups per scan thread
     static_assert(kIPT % 4 == 0 && 16 * kIPT <= 256, "ranks are packed four to a register (< 256 each)");
     static_assert(kGroups % kH == 0, "scan threads split the groups evenly");
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* s_tbl = reinterpret_cast<uint32_t*>(smem);                         // [kGroups][256]
-    uint2* s_pairs = reinterpret_cast<uint2*>(smem + SM::kTblBytes);             // kHasValues
-    uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem + SM::kTblBytes);        // !kHasValues
+    uint2* s_pairs = reinterpret_cast<uint2*>(smem + SM::kTblBytes);             // 32-bit keys with values: {key, value}
+    KeyT* s_keys = reinterpret_cast<KeyT*>(smem + SM::kTblBytes);                // otherwise: keys[tile] | values[tile]
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem + SM::kTblBytes + kTile * (int)sizeof(KeyT));
     uint32_t* s_global_off = reinterpret_cast<uint32_t*>(smem + SM::kTblBytes + SM::kPairBytes);
     uint32_t* s_part = s_global_off + kRadix;                                    // [kH][256]
     uint32_t* s_scan = s_part + kH * kRadix;                                     // [kWarps]
@@ -211,13 +241,13 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     const uint32_t l16 = lane & 15u;
     const uint32_t group = 2u * warp + (lane >> 4);
     const uint32_t item0 = group * (16u * kIPT) + l16;
-    uint32_t key[kIPT];
+    KeyT key[kIPT];
 #ifndef USRT_LAB_SHFL_LOADS
     // direct form: every load touches two 64-byte segments, one per group (two L1 wavefronts instead of one)
 #pragma unroll
     for (int i = 0; i < kIPT; ++i) {
         const uint32_t idx = item0 + (uint32_t)i * 16u;
-        key[i] = idx < valid ? __ldg(keys_in + tile_base + idx) : 0xFFFFFFFFu;   // tail pads sort last, never stored
+        key[i] = idx < valid ? __ldg(keys_in + tile_base + idx) : ~(KeyT)0;      // tail pads sort last, never stored
     }
 #else
     // (measured slower, 0.348 vs 0.334 ms per pass at 2^26: the shuffles cost more than the extra load wavefronts)
@@ -249,7 +279,7 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
         uint32_t out_of_order = flags & 1u;
 #pragma unroll
         for (int i = 0; i < kIPT; ++i) {
-            const uint32_t d = (key[i] >> shift) & 255u;
+            const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
             const uint32_t old = atomicAdd(tbl + d, add);
             __syncwarp();
             atomicSub(tbl + d, bit);
@@ -269,7 +299,7 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
             const uint32_t below = (1u << l16) - 1u;
 #pragma unroll
             for (int i = 0; i < kIPT; ++i) {
-                const uint32_t d = (key[i] >> shift) & 255u;
+                const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
                 atomicAdd(tbl + d, add);
                 __syncwarp();
                 const uint32_t now = tbl[d];                    // every peer of this round has added itself
@@ -350,10 +380,14 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     // stage the tile in digit order
 #pragma unroll
     for (int i = 0; i < kIPT; ++i) {
-        const uint32_t dg = (key[i] >> shift) & 255u;
+        const uint32_t dg = (uint32_t)(key[i] >> shift) & 255u;
         const uint32_t slot = tbl[dg] + ((rank4[i >> 2] >> ((i & 3) * 8)) & 0xFFu);
-        if (kHasValues) s_pairs[slot] = make_uint2(key[i], val[i]);
-        else s_keys[slot] = key[i];
+        if constexpr (kHasValues && !kWide) {
+            s_pairs[slot] = make_uint2((uint32_t)key[i], val[i]);
+        } else {
+            s_keys[slot] = key[i];
+            if (kHasValues) s_vals[slot] = val[i];
+        }
     }
     // Look-back AFTER staging: the aggregate was published before the scan, so by now the preceding
     // tiles have usually posted their inclusive prefixes and the walk resolves in one round trip.
@@ -390,7 +424,7 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     for (int i = 0; i < kIPT; ++i) {
         const uint32_t p = tid + (uint32_t)i * kBlock;
         if (p < valid) {
-            if (kHasValues) {
+            if constexpr (kHasValues && !kWide) {
                 const uint2 kv = s_pairs[p];
                 const uint32_t dg = (kv.x >> shift) & 255u;
                 const uint32_t dst = s_global_off[dg] + p;
@@ -405,8 +439,10 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
                     vals_out[dst] = kv.y;
                 }
             } else {
-                const uint32_t k = s_keys[p];
-                keys_out[s_global_off[(k >> shift) & 255u] + p] = k;
+                const KeyT k = s_keys[p];
+                const uint32_t dst = s_global_off[(uint32_t)(k >> shift) & 255u] + p;
+                keys_out[dst] = k;
+                if (kHasValues) vals_out[dst] = s_vals[p];
             }
         }
     }
@@ -532,7 +568,7 @@ cudaError_t run_pass(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint3
 cudaError_t sort_scratch_reserve(SortScratch& s, uint64_t count, bool need_alt) {
     cudaError_t e;
     if (s.hist == nullptr) {
-        if ((e = cudaMalloc(&s.hist, kSortPasses * kRadix * sizeof(uint32_t))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&s.hist, 2 * kSortPasses * kRadix * sizeof(uint32_t))) != cudaSuccess) return e;   // 8 digits: 64-bit keys
         ++s.generation;
     }
     const uint64_t need = kHeaderWords * 4 + kSortPasses * status_words_bytes(count);
@@ -559,6 +595,8 @@ void sort_scratch_free(SortScratch& s) {
     if (s.status) cudaFree(s.status);
     if (s.keys_alt) cudaFree(s.keys_alt);
     if (s.vals_alt) cudaFree(s.vals_alt);
+    if (s.keys64_alt) cudaFree(s.keys64_alt);
+    if (s.vals64_alt) cudaFree(s.vals64_alt);
     s = SortScratch();
 }
 
@@ -594,6 +632,86 @@ cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint3
         const uint32_t* tk = ki; const uint32_t* tv = vi;
         ki = ko; vi = vo;
         ko = const_cast<uint32_t*>(tk); vo = const_cast<uint32_t*>(tv);
+    }
+    return cudaSuccess;   // even number of passes: the result is back in (keys, vals)
+}
+
+// ---- ComputeBufferSorter<ulong, uint>: 8 passes x 8 bits over 64-bit keys (ComputeBufferSorter.cs:179-191) -----------
+namespace {
+using Tile64 = TileCfg<512, 8, 2>;                   // 4096 pairs: 64-bit keys take two registers each
+inline uint32_t num_tiles64(uint64_t count) { return (uint32_t)((count + Tile64::kTile - 1) / Tile64::kTile); }
+inline uint64_t status_bytes64(uint64_t count) { return (uint64_t)num_tiles64(count) * kRadix * (wide_status(count) ? 8 : 4); }
+
+template <typename StatusT, bool kHasValues>
+cudaError_t launch_pass64(const uint64_t* ki, const uint32_t* vi, uint64_t* ko, uint32_t* vo, uint64_t count, int shift,
+                          const uint32_t* digit_base, uint32_t* tile_counter, void* status, cudaStream_t stream) {
+    constexpr int smem = PassSmem<Tile64, kHasValues, 8>::kTotal;
+    auto kern = k_onesweep<Tile64, StatusT, kHasValues, false, uint64_t>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<num_tiles64(count), Tile64::kBlock, smem, stream>>>(ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter,
+                                                               static_cast<StatusT*>(status), pass_flags(), nullptr, nullptr);
+    return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t sort_scratch_reserve64(SortScratch& s, uint64_t count, bool need_alt) {
+    cudaError_t e;
+    if ((e = sort_scratch_reserve(s, 1, false)) != cudaSuccess) return e;          // hist
+    const uint64_t need = kHeaderWords * 4 + 2 * kSortPasses * status_bytes64(count);
+    if (need > s.status_bytes) {
+        if (s.status) cudaFree(s.status);
+        s.status = nullptr; s.status_bytes = 0;
+        if ((e = cudaMalloc(&s.status, need)) != cudaSuccess) return e;
+        s.status_bytes = need;
+        ++s.generation;
+    }
+    if (need_alt && count > s.alt64_capacity) {
+        if (s.keys64_alt) cudaFree(s.keys64_alt);
+        if (s.vals64_alt) cudaFree(s.vals64_alt);
+        s.keys64_alt = nullptr; s.vals64_alt = nullptr; s.alt64_capacity = 0;
+        if ((e = cudaMalloc(&s.keys64_alt, count * 8)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&s.vals64_alt, count * 4)) != cudaSuccess) return e;
+        s.alt64_capacity = count;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t sort_pairs64(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt, uint64_t count, SortScratch& s,
+                         cudaStream_t stream, uint64_t* launches) {
+    if (count == 0) return cudaSuccess;
+    cudaError_t e;
+    if ((e = sort_scratch_reserve64(s, count, false)) != cudaSuccess) return e;
+    constexpr int kPasses = 2 * kSortPasses;
+    const uint64_t pass_bytes = status_bytes64(count);
+    if ((e = cudaMemsetAsync(s.hist, 0, kPasses * kRadix * 4, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.status, 0, kHeaderWords * 4 + kPasses * pass_bytes, stream)) != cudaSuccess) return e;
+    cudaFuncSetAttribute(k_histogram64, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((count + kHistThreads - 1) / kHistThreads, 1), (uint64_t)kNumSMs);
+    for (int half = 0; half < 2; ++half) {
+        k_histogram64<<<grid, kHistThreads, kHistSmemBytes, stream>>>(reinterpret_cast<const uint2*>(keys), count, half,
+                                                                       s.hist + half * kSortPasses * kRadix);
+        k_scan_histogram<<<1, kSortPasses * kRadix, 0, stream>>>(s.hist + half * kSortPasses * kRadix, nullptr, -1);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (launches) *launches += 4;
+    uint32_t* counters = static_cast<uint32_t*>(s.status);
+    char* status0 = static_cast<char*>(s.status) + kHeaderWords * 4;
+    const uint64_t* ki = keys; const uint32_t* vi = vals;
+    uint64_t* ko = keys_alt; uint32_t* vo = vals_alt;
+    for (int pass = 0; pass < kPasses; ++pass) {                    // bitOffset = 0, 8, ..., 56
+        void* st = status0 + (uint64_t)pass * pass_bytes;
+        const bool wide = wide_status(count);
+        if (vi != nullptr)
+            e = wide ? launch_pass64<uint64_t, true>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream)
+                     : launch_pass64<uint32_t, true>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream);
+        else
+            e = wide ? launch_pass64<uint64_t, false>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream)
+                     : launch_pass64<uint32_t, false>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream);
+        if (e != cudaSuccess) return e;
+        if (launches) *launches += 1;
+        const uint64_t* tk = ki; const uint32_t* tv = vi;
+        ki = ko; vi = vo;
+        ko = const_cast<uint64_t*>(tk); vo = const_cast<uint32_t*>(tv);
     }
     return cudaSuccess;   // even number of passes: the result is back in (keys, vals)
 }
@@ -652,12 +770,12 @@ cudaError_t partition_scatter(const uint32_t* src_keys, const uint32_t* src_vals
         constexpr int smem = PassSmem<SmallTile, true>::kTotal;
         cudaFuncSetAttribute(k_onesweep<SmallTile, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         k_onesweep<SmallTile, uint32_t, true, true><<<num_tiles(count), SmallTile::kBlock, smem, stream>>>(
-            src_keys, src_vals, nullptr, nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, pass_flags(), key_ptrs, val_ptrs);
+            src_keys, src_vals, static_cast<uint32_t*>(nullptr), nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, pass_flags(), key_ptrs, val_ptrs);
     } else {
         constexpr int smem = PassSmem<BigTile, true>::kTotal;
         cudaFuncSetAttribute(k_onesweep<BigTile, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         k_onesweep<BigTile, uint32_t, true, true><<<num_tiles(count), BigTile::kBlock, smem, stream>>>(
-            src_keys, src_vals, nullptr, nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, pass_flags(), key_ptrs, val_ptrs);
+            src_keys, src_vals, static_cast<uint32_t*>(nullptr), nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, pass_flags(), key_ptrs, val_ptrs);
     }
     if (launches) *launches += 1;
     return cudaGetLastError();

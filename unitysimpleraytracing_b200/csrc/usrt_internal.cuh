@@ -24,7 +24,10 @@ struct SortScratch {
     uint32_t* keys_alt = nullptr;      // ping-pong partners for the standalone sorter
     uint32_t* vals_alt = nullptr;
     uint64_t alt_capacity = 0;         // elements
-    uint32_t* hist = nullptr;          // [4][256] digit histograms, then exclusive digit bases
+    uint64_t* keys64_alt = nullptr;    // the same for the 64-bit-key sorter
+    uint32_t* vals64_alt = nullptr;
+    uint64_t alt64_capacity = 0;
+    uint32_t* hist = nullptr;          // [8][256] digit histograms (4 used by 32-bit keys), then exclusive digit bases
     void* status = nullptr;            // [4 tile counters (as 64 x u32 header)] + [passes][tiles][256] look-back words
     uint64_t status_bytes = 0;
     uint64_t generation = 0;           // bumped whenever hist / status are (re)allocated: captured graphs hold these pointers
@@ -35,6 +38,10 @@ struct SortScratch {
 // events (optional, 6): recorded before the histogram, after it, and after each of the 4 passes.
 cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt, uint64_t count,
                        SortScratch& scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events = nullptr);
+// 64-bit keys, 8 passes; same contract (ComputeBufferSorter<ulong, uint>)
+cudaError_t sort_pairs64(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt, uint64_t count, SortScratch& scratch,
+                         cudaStream_t stream, uint64_t* launches);
+cudaError_t sort_scratch_reserve64(SortScratch& scratch, uint64_t count, bool need_alt);
 // One stable partition pass src -> dst by digit (key >> bit_offset) & 255.
 cudaError_t partition_pass(const uint32_t* src_keys, const uint32_t* src_vals, uint32_t* dst_keys, uint32_t* dst_vals,
                            uint64_t count, int bit_offset, uint32_t* histogram_out, SortScratch& scratch,
@@ -64,8 +71,16 @@ cudaError_t launch_distribute_keys(const uint32_t* src, uint32_t* dst, uint32_t 
                                    cudaStream_t stream, int* launches);
 uint64_t distribute_status_bytes(uint32_t n);
 // K4
-cudaError_t launch_construct_tree(const uint32_t* keys, uint32_t n, usrt_internal_node* internal,
+// key_mode 0: 32-bit keys made unique by DistributeKeys (the reference); 1: 32-bit Morton codes with ties broken by
+// sorted position (no DistributeKeys); 2: 64-bit keys (keys = const uint64_t*) made unique by the 64-bit DistributeKeys
+cudaError_t launch_construct_tree(const void* keys, int key_mode, uint32_t n, usrt_internal_node* internal,
                                   usrt_leaf_node* leaf, uint32_t* up_internal, uint32_t* up_leaf, cudaStream_t stream);
+cudaError_t launch_distribute_keys64(const uint64_t* src, uint64_t* dst, uint32_t n, void* scan_status, cudaStream_t stream,
+                                     int* launches);
+uint64_t distribute_status_bytes64(uint32_t n);
+// K1 with 21 bits per axis: 63-bit Morton keys
+cudaError_t launch_morton64(const usrt_triangle* tris, uint32_t n, const WorldBox& whole, uint64_t* keys, uint32_t* values,
+                            usrt_aabb* aabbs, cudaStream_t stream);
 // K5 (+ packed traversal arrays)
 cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
                                  const usrt_triangle* tris, const usrt_internal_node* internal,

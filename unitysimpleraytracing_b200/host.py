@@ -24,7 +24,7 @@ from .scene_types import AABB, InternalNode, LeafNode, RaycastResult, Triangle
 _BUF_DTYPES = {
     _lib.BUF_KEYS: np.dtype("<u4"), _lib.BUF_TRIANGLE_INDEX: np.dtype("<u4"), _lib.BUF_TRIANGLE_DATA: Triangle,
     _lib.BUF_TRIANGLE_AABB: AABB, _lib.BUF_BVH_DATA: AABB, _lib.BUF_LEAF_NODES: LeafNode,
-    _lib.BUF_INTERNAL_NODES: InternalNode,
+    _lib.BUF_INTERNAL_NODES: InternalNode, _lib.BUF_KEYS64: np.dtype("<u8"),
 }
 
 
@@ -83,6 +83,10 @@ class Context:
             stream = torch.cuda.current_stream(self.device)
         self.set_stream(stream.cuda_stream or 1)
 
+    def set_key_mode(self, mode):
+        """_lib.KEYS_REFERENCE (default) / KEYS_INDEX_TIEBREAK / KEYS_MORTON64 (include/usrt.h usrt_key_mode)."""
+        self._check(self._lib.usrt_set_key_mode(self._h, int(mode)))
+
     def set_world_bounds(self, whole_min, whole_max):
         self._check(self._lib.usrt_set_world_bounds(self._h, whole_min, whole_max))
 
@@ -132,6 +136,17 @@ class Context:
         if values is not None:
             assert values.dtype == np.uint32 and values.flags.c_contiguous and len(values) == len(keys)
         self._check(self._lib.usrt_sort_pairs_host(self._h, _ptr(keys), _ptr(values), len(keys)))
+
+    def sort_pairs64_host(self, keys, values=None):
+        """ComputeBufferSorter<ulong, uint>: in place on contiguous uint64 keys / uint32 values."""
+        assert keys.dtype == np.uint64 and keys.flags.c_contiguous
+        if values is not None:
+            assert values.dtype == np.uint32 and values.flags.c_contiguous and len(values) == len(keys)
+        self._check(self._lib.usrt_sort_pairs64_host(self._h, _ptr(keys), _ptr(values), len(keys)))
+
+    def sort_pairs64_device(self, keys_ptr, values_ptr, count):
+        self._check(self._lib.usrt_sort_pairs64_device(self._h, ctypes.c_void_p(keys_ptr),
+                                                       ctypes.c_void_p(values_ptr) if values_ptr else None, count))
 
     def sort_pairs_device(self, keys_ptr, values_ptr, count):
         self._check(self._lib.usrt_sort_pairs_device(self._h, ctypes.c_void_p(keys_ptr),
