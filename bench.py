@@ -474,6 +474,38 @@ def run_ours(args):
     e2e_ms = statistics.median(e2e_blocks)
     checks["e2e_frame_equals_device_frame"] = bool(hits_h[1].tobytes() == gpu_frame.tobytes())
 
+    # the same pipeline with the ADDITIVE positions-only upload (usrt_upload_positions_async: 48 of the 128 bytes of every
+    # Triangle, all the build and the traversal read) -- reported beside the full-struct number, not instead of it
+    pinned_pos = torch.from_numpy(np.ascontiguousarray(tris.view(np.float32).reshape(n, 32)[:, :12])).pin_memory()
+    pos_h = pinned_pos.numpy()
+
+    def e2e_pos_run(k):
+        for i in range(k):
+            c = E[i % 2]
+            c.sync()
+            c.upload_positions(pos_h, pinned=True)
+            c.rebuild()
+            c.trace_primary_async(W, H, cam["near"], cam["tan_half_fov"], m, hits_h[i % 2])
+        for c in E:
+            c.sync()
+
+    e2e_pos_run(4)
+    e2e_pos_blocks = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        e2e_pos_run(e2e_steps)
+        torch.cuda.synchronize()
+        e2e_pos_blocks.append(max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3))
+    e2e_pos_ms = statistics.median(e2e_pos_blocks)
+    if os.environ.get("USRT_BENCH_DEBUG"):
+        sys.stderr.write("e2e blocks %s pos blocks %s\n" % (e2e_blocks, e2e_pos_blocks))
+    checks["e2e_positions_only_frame_equals_device_frame"] = bool(hits_h[1].tobytes() == gpu_frame.tobytes() and
+                                                                   hits_h[0].tobytes() == gpu_frame.tobytes())
+    for c in E:
+        c.upload_triangles(tris_h)         # back to the full-struct source for the legs below
+    del pinned_pos
+
     line = None
     e2e_sync_ms = None
     if rank == 0:
@@ -623,6 +655,10 @@ def run_ours(args):
             "e2e": {"value": world * rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": int(rays * 16), "ranks": world,
                     "synchronous_ms_per_step": e2e_sync_ms, "synchronous_value": rays / (e2e_sync_ms * 1e-3) / 1e6,
+                    "positions_only": {"value": world * rays / (e2e_pos_ms * 1e-3) / 1e6, "ms_per_step": e2e_pos_ms,
+                                       "h2d_bytes_per_step": int(n * 48), "d2h_bytes_per_step": int(rays * 16),
+                                       "note": "additive API usrt_upload_positions_async: the 48 bytes per triangle the build and "
+                                               "the traversal read; same frames, bit for bit"},
                     "note": "per frame and per rank: usrt_upload_triangles_async(pinned host) + usrt_rebuild + "
                             "usrt_trace_primary_async(pinned host frame), frames alternate over two contexts so the next upload "
                             "overlaps the kernels; every rank runs it at once, value = all ranks' rays / the slowest rank's wall "

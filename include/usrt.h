@@ -109,6 +109,13 @@ int usrt_upload_triangles(usrt_context* ctx, const usrt_triangle* host_triangles
 /* Same, asynchronous: host_triangles must be page-locked and stay untouched until usrt_sync (or a later
  * synchronising call) returns. With two contexts on one GPU, frame i+1's upload overlaps frame i's kernels. */
 int usrt_upload_triangles_async(usrt_context* ctx, const usrt_triangle* pinned_host_triangles, uint32_t n);
+/* ADDITIVE to the reference's SetData of whole Triangle structs (MeshBufferContainer.cs:150): positions only -- 12 floats
+ * per triangle, exactly the first 48 bytes of usrt_triangle (a.xyz, pad, b.xyz, pad, c.xyz, pad). Those are the only bytes the
+ * build and the traversal ever read, so an animated mesh can re-send 48 instead of 128 bytes per triangle per frame. The
+ * Triangle array keeps whatever was uploaded last (uv / normals for usrt_shade); hit records, nodes and boxes are
+ * bit-identical to a full upload of the same positions. _async: page-locked memory, untouched until usrt_sync. */
+int usrt_upload_positions(usrt_context* ctx, const float* host_positions, uint32_t n);
+int usrt_upload_positions_async(usrt_context* ctx, const float* pinned_host_positions, uint32_t n);
 /* Same, from a DEVICE pointer (async, device-to-device). */
 int usrt_set_triangles_device(usrt_context* ctx, const void* dev_triangles, uint32_t n);
 /* K1 -- the CPU loop of MeshBufferContainer.cs:123-146 as a kernel: padded AABB, centroid of the padded

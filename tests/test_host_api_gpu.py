@@ -311,3 +311,42 @@ def test_partial_trace_then_shade_sees_misses_not_garbage(usrt, oracle):
     full = oracle.Scene(tris).trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
     assert part[20 * w:30 * w].tobytes() == full[20 * w:30 * w].tobytes()
     ctx.close()
+
+
+def _positions_of(tris):
+    """First 48 bytes of every Triangle as (n, 12) float32: a.xyz, pad, b.xyz, pad, c.xyz, pad."""
+    return np.ascontiguousarray(tris.view(np.float32).reshape(len(tris), 32)[:, :12])
+
+
+def test_positions_only_upload_is_bit_identical_to_a_full_upload(usrt, oracle):
+    """usrt_upload_positions (48 B/triangle) feeds the build and the traversal exactly what they read of a Triangle;
+    every buffer, hit record and bounce ray equals the full-struct path, also when the two are interleaved."""
+    import torch
+    a, b = meshes.uniform_soup(30000, seed=31), meshes.uniform_soup(30000, seed=32)
+    ra, rb = oracle.Scene(a), oracle.Scene(b)
+    cam = meshes.SCENE_SOUP_CAMERA
+    ctx = usrt.Context(30000)
+    ctx.upload_triangles(a); ctx.rebuild(); ctx.rebuild()                       # graph captured on the Triangle source
+    for tris, ref, pinned in ((b, rb, False), (a, ra, True), (b, rb, False)):
+        pos = _positions_of(tris)
+        if pinned:
+            keep = torch.from_numpy(pos).pin_memory(); pos = keep.numpy()
+        ctx.upload_positions(pos, pinned=pinned)
+        ctx.rebuild(); ctx.rebuild()
+        n = len(tris)
+        assert np.array_equal(ctx.download(_lib.BUF_KEYS), ref.sortedMortonCodes)
+        assert ctx.download(_lib.BUF_TRIANGLE_AABB).tobytes() == ref.triangleAABB.tobytes()
+        assert ctx.download(_lib.BUF_INTERNAL_NODES, n - 1).tobytes() == ref.internalNodes[:n - 1].tobytes()
+        assert ctx.download(_lib.BUF_BVH_DATA, n - 1).tobytes() == ref.bvhData[:n - 1].tobytes()
+        hits = ctx.trace_primary(96, 54, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+        assert hits.tobytes() == ref.trace_primary(96, 54, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], threads=4).tobytes()
+        rays = torch.empty(96 * 54 * 8, dtype=torch.float32, device="cuda:0")
+        ctx.diffuse_rays_device(96, 54, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], 77, 0, 1, rays.data_ptr())
+        ctx.sync()
+        want = oracle.diffuse_rays(hits, tris, 96, 54, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], 77, 0, 1)
+        assert rays.cpu().numpy().tobytes() == want.tobytes()
+    ctx.upload_triangles(a); ctx.rebuild()                                        # and back to full structs
+    assert ctx.download(_lib.BUF_BVH_DATA, 29999).tobytes() == ra.bvhData[:29999].tobytes()
+    with pytest.raises(_lib.UsrtError):
+        ctx.upload_positions(np.zeros((30001, 12), np.float32))
+    ctx.close()

@@ -38,6 +38,10 @@ struct usrt_context {
     uint64_t *keys64 = nullptr, *keys64_alt = nullptr, *keys64_primary = nullptr;
     void* scan_status64 = nullptr;
     usrt_triangle* triangles = nullptr;
+    // compact 48-byte position records {a, b, c} per triangle, filled by usrt_upload_positions only (allocated on first use)
+    float4* positions = nullptr;
+    bool positions_only = false;          // the last upload was positions only: K1 reads `positions`, `triangles` is stale
+    bool graph_positions_only = false;
     usrt_aabb* tri_aabb = nullptr;
     usrt_aabb* bvh = nullptr;
     usrt_leaf_node* leaf = nullptr;
@@ -163,11 +167,16 @@ int ensure_rays(usrt_context* ctx, uint64_t count) {
     return USRT_OK;
 }
 
+VertexSource vertex_source(const usrt_context* ctx) {
+    if (ctx->positions_only) return VertexSource{ctx->positions, 3u};
+    return VertexSource{reinterpret_cast<const float4*>(ctx->triangles), 8u};
+}
+
 int do_morton(usrt_context* ctx) {
     if (ctx->key_mode == USRT_KEYS_MORTON64)
-        CU(ctx, launch_morton64(ctx->triangles, ctx->n, ctx->whole, ctx->keys64, ctx->tri_index, ctx->tri_aabb, ctx->stream));
+        CU(ctx, launch_morton64(vertex_source(ctx), ctx->n, ctx->whole, ctx->keys64, ctx->tri_index, ctx->tri_aabb, ctx->stream));
     else
-        CU(ctx, launch_morton(ctx->triangles, ctx->n, ctx->whole, ctx->keys, ctx->tri_index, ctx->tri_aabb, ctx->stream));
+        CU(ctx, launch_morton(vertex_source(ctx), ctx->n, ctx->whole, ctx->keys, ctx->tri_index, ctx->tri_aabb, ctx->stream));
     ctx->launches += 1;
     ctx->stage = ST_TRIS | ST_MORTON;
     return USRT_OK;
@@ -211,7 +220,7 @@ int do_tree(usrt_context* ctx) {
 }
 
 int do_bvh(usrt_context* ctx) {
-    CU(ctx, launch_construct_bvh(ctx->n, ctx->tri_index, ctx->tri_aabb, ctx->triangles, ctx->internal, ctx->up_internal,
+    CU(ctx, launch_construct_bvh(ctx->n, ctx->tri_index, ctx->tri_aabb, vertex_source(ctx), ctx->internal, ctx->up_internal,
                                  ctx->up_leaf, ctx->bvh, ctx->slots, ctx->packed_nodes, ctx->packed_tris, ctx->stream));
     ctx->launches += 1;
     ctx->stage |= ST_BVH;
@@ -283,7 +292,7 @@ int usrt_destroy(usrt_context* ctx) {
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     void* ptrs[] = {ctx->keys, ctx->keys_alt, ctx->tri_index, ctx->tri_index_alt, ctx->triangles, ctx->tri_aabb,
-                    ctx->bvh, ctx->leaf, ctx->internal, ctx->slots, ctx->up_internal, ctx->up_leaf, ctx->packed_nodes, ctx->packed_tris,
+                    ctx->positions, ctx->bvh, ctx->leaf, ctx->internal, ctx->slots, ctx->up_internal, ctx->up_leaf, ctx->packed_nodes, ctx->packed_tris,
                     ctx->scan_status, ctx->scan_status64, ctx->keys64, ctx->keys64_alt, ctx->small, ctx->scene_box, ctx->hits, ctx->rays, ctx->texture, ctx->shaded};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -337,7 +346,7 @@ int usrt_fit_world_box(usrt_context* ctx, float out_min[3], float out_max[3]) {
     if (!(ctx->stage & ST_TRIS) || ctx->n == 0) return fail(ctx, USRT_ERR_STATE, "fit_world_box: no triangles uploaded");
     if (int r = bind_device(ctx)) return r;
     if (!ctx->scene_box) CU(ctx, cudaMalloc(&ctx->scene_box, 6 * sizeof(float)));
-    CU(ctx, launch_scene_box(ctx->triangles, ctx->n, ctx->scene_box, ctx->stream));
+    CU(ctx, launch_scene_box(vertex_source(ctx), ctx->n, ctx->scene_box, ctx->stream));
     ctx->launches += 1;
     float b[6];
     CU(ctx, cudaMemcpyAsync(b, ctx->scene_box, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream));
@@ -366,6 +375,7 @@ int usrt_upload_triangles(usrt_context* ctx, const usrt_triangle* host_triangles
     ctx->dirty_n = n;
     CU(ctx, cudaMemcpyAsync(ctx->triangles, host_triangles, (size_t)n * sizeof(usrt_triangle), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->positions_only = false;
     ctx->n = n;
     ctx->stage = ST_TRIS;
     return USRT_OK;
@@ -384,6 +394,7 @@ int usrt_upload_triangles_async(usrt_context* ctx, const usrt_triangle* pinned_h
     if (int r = reset_scene_buffers(ctx, n, ctx->dirty_n)) return r;
     ctx->dirty_n = n;
     CU(ctx, cudaMemcpyAsync(ctx->triangles, pinned_host_triangles, (size_t)n * sizeof(usrt_triangle), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->positions_only = false;
     ctx->n = n;
     ctx->stage = ST_TRIS;
     return USRT_OK;
@@ -396,9 +407,43 @@ int usrt_set_triangles_device(usrt_context* ctx, const void* dev_triangles, uint
     if (int r = reset_scene_buffers(ctx, n, ctx->dirty_n)) return r;
     ctx->dirty_n = n;
     CU(ctx, cudaMemcpyAsync(ctx->triangles, dev_triangles, (size_t)n * sizeof(usrt_triangle), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->positions_only = false;
     ctx->n = n;
     ctx->stage = ST_TRIS;
     return USRT_OK;
+}
+
+// Positions only: 48 bytes per triangle instead of 128. Everything the build and the traversal read of a Triangle is its
+// first 48 bytes (a, b, c); uv / normals matter to the shading epilogue alone.
+static int upload_positions(usrt_context* ctx, const void* host_positions, uint32_t n, bool async) {
+    if (!host_positions || n > ctx->capacity) return fail(ctx, USRT_ERR_ARG, "upload_positions: n=%u capacity=%u", n, ctx->capacity);
+    if (int r = bind_device(ctx)) return r;
+    if (async) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, host_positions) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            return fail(ctx, USRT_ERR_ARG, "upload_positions_async: host memory must be page-locked");
+        }
+    }
+    if (!ctx->positions) CU(ctx, cudaMalloc(&ctx->positions, (size_t)ctx->capacity * 3 * sizeof(float4)));
+    if (int r = reset_scene_buffers(ctx, n, ctx->dirty_n)) return r;
+    ctx->dirty_n = n;
+    CU(ctx, cudaMemcpyAsync(ctx->positions, host_positions, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
+    if (!async) CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->positions_only = true;
+    ctx->n = n;
+    ctx->stage = ST_TRIS;
+    return USRT_OK;
+}
+
+int usrt_upload_positions(usrt_context* ctx, const float* host_positions, uint32_t n) {
+    NEED_CTX(ctx);
+    return upload_positions(ctx, host_positions, n, false);
+}
+
+int usrt_upload_positions_async(usrt_context* ctx, const float* pinned_host_positions, uint32_t n) {
+    NEED_CTX(ctx);
+    return upload_positions(ctx, pinned_host_positions, n, true);
 }
 
 int usrt_upload_bvh(usrt_context* ctx, uint32_t n, const uint32_t* keys, const uint32_t* triangle_index,
@@ -436,6 +481,7 @@ int usrt_upload_bvh(usrt_context* ctx, uint32_t n, const uint32_t* keys, const u
     CU(ctx, launch_pack_traversal(n, ctx->tri_index, ctx->tri_aabb, ctx->triangles, ctx->internal, ctx->leaf, ctx->bvh,
                                   ctx->packed_nodes, ctx->packed_tris, ctx->stream));
     ctx->launches += 1;
+    ctx->positions_only = false;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n = n;
     // ConstructBVH refits by leaf slot (BVH.compute:199-208): allowed again on this tree only if every leaf sits in its
@@ -723,7 +769,7 @@ int usrt_rebuild(usrt_context* ctx) {
     // context ever saw re-allocates it, which bumps sort.generation and forces a re-capture here)
     CU(ctx, sort_scratch_reserve(ctx->sort, ctx->n, false));              // no allocation while capturing
     if (!ctx->graph_exec || ctx->graph_n != ctx->n || ctx->graph_stream != ctx->stream ||
-        ctx->graph_sort_generation != ctx->sort.generation) {
+        ctx->graph_sort_generation != ctx->sort.generation || ctx->graph_positions_only != ctx->positions_only) {
         drop_rebuild_graph(ctx);
         const uint64_t before = ctx->launches;
         cudaGraph_t graph = nullptr;
@@ -751,6 +797,7 @@ int usrt_rebuild(usrt_context* ctx) {
         ctx->graph_n = ctx->n;
         ctx->graph_stream = ctx->stream;
         ctx->graph_sort_generation = ctx->sort.generation;
+        ctx->graph_positions_only = ctx->positions_only;
         if (ctx->keys != ctx->keys_primary) std::swap(ctx->keys, ctx->keys_alt);   // capture advanced the host-side state
     }
     CU(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
@@ -945,7 +992,7 @@ int usrt_diffuse_rays_device(usrt_context* ctx, int width, int height, float nea
     memcpy(p.m, camera_to_world, sizeof(p.m));
     p.y0 = 0; p.y1 = height;
     p.block_rows = 1; p.shard = 0; p.num_shards = 0; p.local_rows = 0;
-    CU(ctx, launch_diffuse_rays(p, hits, ctx->triangles, seed, first_sample, num_samples, static_cast<float4*>(dev_rays_out), ctx->stream));
+    CU(ctx, launch_diffuse_rays(p, hits, vertex_source(ctx), seed, first_sample, num_samples, static_cast<float4*>(dev_rays_out), ctx->stream));
     ctx->launches += num_samples ? 1 : 0;
     return USRT_OK;
 }

@@ -324,7 +324,7 @@ __device__ __forceinline__ float4 atom_exch_128(float4* p, float4 v) {
 // their boxes through 128-bit atomic exchanges instead of a counter + fence + reload.
 __global__ void __launch_bounds__(kRefitBlock) k_construct_bvh(uint32_t n, const uint32_t* __restrict__ sorted_indices,
                                                                const float4* __restrict__ tri_aabb,
-                                                               const float4* __restrict__ tris,
+                                                               VertexSource vertices,
                                                                const usrt_internal_node* __restrict__ internal,
                                                                const uint32_t* __restrict__ up_internal,
                                                                const uint32_t* __restrict__ up_leaf,
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kRefitBlock) k_construct_bvh(uint32_t n, const
         // The leaf needs its triangle's vertices anyway (traversal-side copy in leaf order, triangle id in
         // a.w), so its padded box is recomputed from them with K1's exact operations
         // (MeshBufferContainer.cs:52-63) instead of gathering the 32-byte triangleAABB entry as well.
-        const float4* t = tris + (size_t)tri * 8;
+        const float4* t = vertices.base + (size_t)tri * vertices.stride;
         float4 a = __ldg(t + 0), b = __ldg(t + 1), c = __ldg(t + 2);
         bmin = make_float4(__fsub_rn(sel_min(sel_min(a.x, b.x), c.x), 0.001f), __fsub_rn(sel_min(sel_min(a.y, b.y), c.y), 0.001f),
                            __fsub_rn(sel_min(sel_min(a.z, b.z), c.z), 0.001f), 0.0f);
@@ -610,11 +610,11 @@ cudaError_t launch_construct_tree(const void* keys, int key_mode, uint32_t n, us
 }
 
 cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
-                                 const usrt_triangle* tris, const usrt_internal_node* internal,
+                                 VertexSource vertices, const usrt_internal_node* internal,
                                  const uint32_t* up_internal, const uint32_t* up_leaf, usrt_aabb* bvh, float4* slots,
                                  float4* packed_nodes, float4* packed_tris, cudaStream_t stream) {
     k_construct_bvh<<<(n + kRefitBlock - 1) / kRefitBlock, kRefitBlock, 0, stream>>>(
-        n, sorted_indices, reinterpret_cast<const float4*>(tri_aabb), reinterpret_cast<const float4*>(tris), internal,
+        n, sorted_indices, reinterpret_cast<const float4*>(tri_aabb), vertices, internal,
         up_internal, up_leaf, reinterpret_cast<float4*>(bvh), slots, packed_nodes, packed_tris);
     return cudaGetLastError();
 }

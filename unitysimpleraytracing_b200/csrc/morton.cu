@@ -46,12 +46,12 @@ __device__ __forceinline__ uint32_t quantise21(float x) {
 }
 
 template <bool kWide>
-__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ tris, uint32_t n, WorldBox whole,
+__global__ void __launch_bounds__(256) k_morton(VertexSource src, uint32_t n, WorldBox whole,
                                                 uint32_t* __restrict__ keys, uint64_t* __restrict__ keys64,
                                                 uint32_t* __restrict__ values, float4* __restrict__ aabbs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4* t = tris + (size_t)i * 8;       // 128-B Triangle = 8 x float4; a, b, c are slots 0..2
+    const float4* t = src.base + (size_t)i * src.stride;   // 128-B Triangle = 8 x float4 (or a 48-B record); a, b, c are slots 0..2
     const float4 a = __ldg(t + 0), b = __ldg(t + 1), c = __ldg(t + 2);
 
     // GetCentroidAndAABB (:52-71)
@@ -94,10 +94,10 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
     else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-__global__ void __launch_bounds__(256) k_scene_box(const float4* __restrict__ tris, uint32_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_scene_box(VertexSource src, uint32_t n, float* __restrict__ out) {
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4* t = tris + (size_t)i * 8;
+        const float4* t = src.base + (size_t)i * src.stride;
         const float4 a = __ldg(t + 0), b = __ldg(t + 1), c = __ldg(t + 2);
         mn[0] = sel_min(mn[0], sel_min(sel_min(a.x, b.x), c.x)); mx[0] = sel_max(mx[0], sel_max(sel_max(a.x, b.x), c.x));
         mn[1] = sel_min(mn[1], sel_min(sel_min(a.y, b.y), c.y)); mx[1] = sel_max(mx[1], sel_max(sel_max(a.y, b.y), c.y));
@@ -117,30 +117,26 @@ __global__ void __launch_bounds__(256) k_scene_box(const float4* __restrict__ tr
     }
 }
 
-cudaError_t launch_scene_box(const usrt_triangle* tris, uint32_t n, float* out6, cudaStream_t stream) {
+cudaError_t launch_scene_box(VertexSource src, uint32_t n, float* out6, cudaStream_t stream) {
     static const float init[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     cudaError_t e = cudaMemcpyAsync(out6, init, sizeof(init), cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess || n == 0) return e;
     const uint32_t grid = std::min<uint32_t>((n + 255) / 256, 148 * 8);
-    k_scene_box<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(tris), n, out6);
+    k_scene_box<<<grid, 256, 0, stream>>>(src, n, out6);
     return cudaGetLastError();
 }
 
-cudaError_t launch_morton(const usrt_triangle* tris, uint32_t n, const WorldBox& whole, uint32_t* keys,
-                          uint32_t* values, usrt_aabb* aabbs, cudaStream_t stream) {
+cudaError_t launch_morton(VertexSource src, uint32_t n, const WorldBox& whole, uint32_t* keys, uint32_t* values, usrt_aabb* aabbs,
+                          cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    const uint32_t block = 256;
-    const uint32_t grid = (n + block - 1) / block;
-    k_morton<false><<<grid, block, 0, stream>>>(reinterpret_cast<const float4*>(tris), n, whole, keys, nullptr, values,
-                                                reinterpret_cast<float4*>(aabbs));
+    k_morton<false><<<(n + 255) / 256, 256, 0, stream>>>(src, n, whole, keys, nullptr, values, reinterpret_cast<float4*>(aabbs));
     return cudaGetLastError();
 }
 
-cudaError_t launch_morton64(const usrt_triangle* tris, uint32_t n, const WorldBox& whole, uint64_t* keys, uint32_t* values,
+cudaError_t launch_morton64(VertexSource src, uint32_t n, const WorldBox& whole, uint64_t* keys, uint32_t* values,
                             usrt_aabb* aabbs, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    k_morton<true><<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float4*>(tris), n, whole, nullptr, keys, values,
-                                                        reinterpret_cast<float4*>(aabbs));
+    k_morton<true><<<(n + 255) / 256, 256, 0, stream>>>(src, n, whole, nullptr, keys, values, reinterpret_cast<float4*>(aabbs));
     return cudaGetLastError();
 }
 

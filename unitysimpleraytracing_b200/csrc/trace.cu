@@ -337,7 +337,7 @@ __device__ __forceinline__ uint64_t hash_u64(uint64_t x) {             // splitm
 }
 
 __global__ void __launch_bounds__(256) k_diffuse_rays(PrimaryParams p, const usrt_raycast_result* __restrict__ hits,
-                                                      const float4* __restrict__ tris, uint64_t seed, uint32_t s0,
+                                                      VertexSource vertices, uint64_t seed, uint32_t s0,
                                                       uint64_t total, float4* __restrict__ rays_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256) k_diffuse_rays(PrimaryParams p, const usr
         const Ray r = primary_ray(p, x, y);
         const float t = h.x;
         const float px = add(r.ox, mul(r.dx, t)), py = add(r.oy, mul(r.dy, t)), pz = add(r.oz, mul(r.dz, t));
-        const float4* tri = tris + (size_t)__float_as_uint(h.y) * 8;
+        const float4* tri = vertices.base + (size_t)__float_as_uint(h.y) * vertices.stride;
         const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
         const float e1x = sub(b.x, a.x), e1y = sub(b.y, a.y), e1z = sub(b.z, a.z);
         const float e2x = sub(c.x, a.x), e2y = sub(c.y, a.y), e2z = sub(c.z, a.z);
@@ -422,12 +422,11 @@ cudaError_t launch_trace_rays(const TraceScene& scene, const float4* rays, uint6
     return cudaGetLastError();
 }
 
-cudaError_t launch_diffuse_rays(const PrimaryParams& p, const usrt_raycast_result* hits, const usrt_triangle* tris,
+cudaError_t launch_diffuse_rays(const PrimaryParams& p, const usrt_raycast_result* hits, VertexSource vertices,
                                 uint64_t seed, uint32_t s0, uint32_t s_count, float4* rays_out, cudaStream_t stream) {
     const uint64_t total = (uint64_t)p.width * (uint64_t)p.height * (uint64_t)s_count;
     if (total == 0) return cudaSuccess;
-    k_diffuse_rays<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, hits, reinterpret_cast<const float4*>(tris), seed, s0,
-                                                                         total, rays_out);
+    k_diffuse_rays<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, hits, vertices, seed, s0, total, rays_out);
     return cudaGetLastError();
 }
 

@@ -62,10 +62,17 @@ void sort_scratch_free(SortScratch& scratch);
 
 // K1
 struct WorldBox { float min[3], max[3]; };            // NormalizeCentroid's box, per axis
-cudaError_t launch_morton(const usrt_triangle* tris, uint32_t n, const WorldBox& whole, uint32_t* keys,
-                          uint32_t* values, usrt_aabb* aabbs, cudaStream_t stream);
+// Where K1 reads the three vertices of triangle i: base + i * stride float4s, a / b / c in slots 0..2. stride 8 = the
+// reference's 128-byte Triangle array; stride 3 = the compact 48-byte position records (usrt_upload_positions).
+struct VertexSource { const float4* base; uint32_t stride; };
+// (Measured: letting K1 also EMIT compact records for K5 costs more than it saves -- K1 34.6 -> 43.0 us for 48 MB of extra
+// writes against K5 102.4 -> 96.3 us at 1M triangles -- so K1, K5 and the bounce-ray generator all read whichever source
+// the caller uploaded.)
+cudaError_t launch_morton(VertexSource src, uint32_t n, const WorldBox& whole, uint32_t* keys, uint32_t* values, usrt_aabb* aabbs,
+                          cudaStream_t stream);
 // per-axis min / max over all vertices -> out6 (device, min xyz then max xyz)
-cudaError_t launch_scene_box(const usrt_triangle* tris, uint32_t n, float* out6, cudaStream_t stream);
+cudaError_t launch_scene_box(VertexSource src, uint32_t n, float* out6, cudaStream_t stream);
+
 // K3 (src != dst; dst receives the distributed keys). scan_status: >= (tiles+1) x 8 bytes, zeroed by the call.
 cudaError_t launch_distribute_keys(const uint32_t* src, uint32_t* dst, uint32_t n, void* scan_status,
                                    cudaStream_t stream, int* launches);
@@ -79,11 +86,11 @@ cudaError_t launch_distribute_keys64(const uint64_t* src, uint64_t* dst, uint32_
                                      int* launches);
 uint64_t distribute_status_bytes64(uint32_t n);
 // K1 with 21 bits per axis: 63-bit Morton keys
-cudaError_t launch_morton64(const usrt_triangle* tris, uint32_t n, const WorldBox& whole, uint64_t* keys, uint32_t* values,
+cudaError_t launch_morton64(VertexSource src, uint32_t n, const WorldBox& whole, uint64_t* keys, uint32_t* values,
                             usrt_aabb* aabbs, cudaStream_t stream);
 // K5 (+ packed traversal arrays)
 cudaError_t launch_construct_bvh(uint32_t n, const uint32_t* sorted_indices, const usrt_aabb* tri_aabb,
-                                 const usrt_triangle* tris, const usrt_internal_node* internal,
+                                 VertexSource vertices, const usrt_internal_node* internal,
                                  const uint32_t* up_internal, const uint32_t* up_leaf, usrt_aabb* bvh, float4* slots,
                                  float4* packed_nodes, float4* packed_tris, cudaStream_t stream);
 // packed traversal arrays from the reference-layout buffers (imported BVH)
@@ -135,7 +142,7 @@ cudaError_t launch_fill_miss(usrt_raycast_result* out, uint64_t count, cudaStrea
 
 // diffuse bounce rays from the primary hit records (BASELINE config 5), s_count samples per pixel starting at s0;
 // ray index = (sample - s0) * W * H + pixel
-cudaError_t launch_diffuse_rays(const PrimaryParams& p, const usrt_raycast_result* hits, const usrt_triangle* tris,
+cudaError_t launch_diffuse_rays(const PrimaryParams& p, const usrt_raycast_result* hits, VertexSource vertices,
                                 uint64_t seed, uint32_t s0, uint32_t s_count, float4* rays_out, cudaStream_t stream);
 
 // shading epilogue

@@ -121,6 +121,14 @@ class Context:
             raise ValueError("upload_triangles_async needs a contiguous Triangle array")
         self._check(self._lib.usrt_upload_triangles_async(self._h, _ptr(pinned_tris), len(pinned_tris)))
 
+    def upload_positions(self, positions, pinned=False):
+        """(n, 12) float32: the first 48 bytes of every Triangle (a.xyz, pad, b.xyz, pad, c.xyz, pad). pinned=True:
+        page-locked memory, asynchronous (untouched until sync())."""
+        pos = positions if pinned else np.ascontiguousarray(positions, np.float32)
+        assert pos.dtype == np.float32 and pos.flags["C_CONTIGUOUS"] and pos.size % 12 == 0
+        fn = self._lib.usrt_upload_positions_async if pinned else self._lib.usrt_upload_positions
+        self._check(fn(self._h, _ptr(pos), pos.size // 12))
+
     def set_triangles_device(self, dev_ptr, n):
         self._check(self._lib.usrt_set_triangles_device(self._h, ctypes.c_void_p(dev_ptr), n))
 
