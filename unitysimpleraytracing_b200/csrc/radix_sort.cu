@@ -40,13 +40,14 @@ template <int BLOCK, int IPT, int CTAS> struct TileCfg {
     static_assert(BLOCK % kRadix == 0, "whole threads per digit in the scan / look-back step");
 };
 #ifndef USRT_BIG_BLOCK                                // (tools/micro/sort_lab.cu builds other shapes side by side)
-#define USRT_BIG_BLOCK 512
-#define USRT_BIG_IPT 16
-#define USRT_BIG_CTAS 2
+#define USRT_BIG_BLOCK 256
+#define USRT_BIG_IPT 24
+#define USRT_BIG_CTAS 3
 #endif
 using BigTile = TileCfg<USRT_BIG_BLOCK, USRT_BIG_IPT, USRT_BIG_CTAS>;   // 8192 pairs
 using SmallTile = TileCfg<256, 8, 6>;               // 2048 pairs
 constexpr uint64_t kSmallSortLimit = 1ull << 18;    // below this many pairs use SmallTile (measured: 2^20 is faster with BigTile)
+constexpr uint64_t kPairsSortLimit = 1ull << 22;    // from this many pairs on, intermediate passes move interleaved records
 constexpr uint32_t kHeaderWords = 64;       // tile counters live in the first 256 B of the status buffer
 
 // look-back status word: flag in the top bits, running count below. 32-bit words hold counts
@@ -184,11 +185,60 @@ __global__ void __launch_bounds__(kSortPasses * kRadix) k_scan_histogram(uint32_
 // warp sync, rank = count - popc(mask) + popc(mask below me)). Each lane then takes its bit out again with a second
 // atomic (no return value). Cost per round of 32 keys: 5.6 SM-cycles against 12.4 for round 1's 64-bit
 // {mask,count} words (atomicOr + 64-bit read + leader write-back) and 25 / 60 for ballot / match.any matching.
+// Order-independent ranking of one warp's keys (the fallback of the trusted flavour below; never taken on B200 unless
+// forced): peers by eight ballots, the running count read by everyone and advanced by the lowest peer. Kept out of line
+// -- it re-reads the keys and hands the ranks over through shared memory -- so that it costs the fast path no registers.
+template <typename KeyT, bool kInPairs>
+__device__ __noinline__ void rank_warp_order_independent(const KeyT* __restrict__ tile_keys, uint32_t valid, uint32_t item0, int items,
+                                                         int shift, uint32_t* tbl, uint16_t* s_rank) {
+    const uint32_t below = lanemask_lt();
+#pragma unroll 1
+    for (int i = 0; i < items; ++i) {
+        const uint32_t idx = item0 + (uint32_t)i * 32u;
+        KeyT key = ~(KeyT)0;
+        if (idx < valid) {
+            if constexpr (kInPairs) key = __ldg(reinterpret_cast<const uint2*>(tile_keys) + idx).x;   // interleaved {key, value}
+            else key = __ldg(tile_keys + idx);
+        }
+        const uint32_t d = (uint32_t)(key >> shift) & 255u;
+        uint32_t peers = 0xFFFFFFFFu;
+#pragma unroll
+        for (int bit = 0; bit < kRadixBits; ++bit) {
+            const bool set = (d >> bit) & 1u;
+            const uint32_t vote = __ballot_sync(0xFFFFFFFFu, set);
+            peers &= set ? vote : ~vote;
+        }
+        const uint32_t prior = tbl[d];
+        __syncwarp();
+        const uint32_t before = __popc(peers & below);
+        if (before == 0) tbl[d] = prior + __popc(peers);
+        __syncwarp();
+        s_rank[idx] = (uint16_t)(prior + before);
+    }
+    __syncwarp();
+}
+
+// Ranking flavour (compile time). 1 (default): whole warps rank with ONE returning atomicAdd per key and trust the
+// hardware's ascending-lane serialisation of same-address shared atomics, which every CTA re-validates on its own SM
+// before it ranks (a canary: 32-way and 8-way conflicts must come back in lane order), falling back to an
+// order-independent ballot ranking for its tile if the canary ever fails. 0: 16-lane groups that additionally carry a
+// lane mask in the word, so EVERY atomic's order is verified, at the price of a second atomic per key (clearing the
+// lane bit), twice the tables and split loads: 0.334 ms per 2^26-pair pass against 0.27 ms (tools/micro/sort_lab.cu).
+#ifndef USRT_RANK_TRUST_LANE_ORDER
+#define USRT_RANK_TRUST_LANE_ORDER 1
+#endif
+constexpr bool kFullWarpRank = USRT_RANK_TRUST_LANE_ORDER != 0;
+#ifndef USRT_LOOKBACK_WINDOW
+#define USRT_LOOKBACK_WINDOW 4
+#endif
+constexpr int kLookBack = USRT_LOOKBACK_WINDOW;   // predecessor status words in flight per look-back round trip
+constexpr int kGroupsPerWarp = kFullWarpRank ? 1 : 2;
+
 template <typename Cfg, bool kHasValues, int kKeyBytes = 4> struct PassSmem {
-    static constexpr int kTblBytes = 2 * Cfg::kWarps * kRadix * 4;
+    static constexpr int kTblBytes = kGroupsPerWarp * Cfg::kWarps * kRadix * 4;
     static constexpr int kPairBytes = Cfg::kTile * (kKeyBytes + (kHasValues ? 4 : 0));
     static constexpr int kH = Cfg::kBlock / kRadix;                      // threads per digit in the scan step
-    static constexpr int kTotal = kTblBytes + kPairBytes + kRadix * 4 + kH * kRadix * 4 + Cfg::kWarps * 4 + 16;
+    static constexpr int kTotal = kTblBytes + kPairBytes + kRadix * 4 + kH * kRadix * 4 + Cfg::kWarps * 4 + 16 + 32;
 };
 
 // kPeer: the multi-GPU bucket exchange. Instead of one output array, every digit has its own base address
@@ -197,7 +247,12 @@ template <typename Cfg, bool kHasValues, int kKeyBytes = 4> struct PassSmem {
 // flags bit 0: test hook, every warp takes the order-independent ranking path.
 // KeyT = uint32_t (the reference's ComputeBufferSorter<uint,uint>) or uint64_t (its GetRadix is generic over uint /
 // ulong, ComputeBufferSorter.cs:179-191): 64-bit keys run 8 passes and stage keys and values in separate arrays.
-template <typename Cfg, typename StatusT, bool kHasValues, bool kPeer = false, typename KeyT = uint32_t>
+// kIO (32-bit keys with values only): how the pairs cross global memory. 0: separate key / value arrays on both sides
+// (the ABI's layout). 1 / 2 / 3: the INTERMEDIATE passes of a 4-pass sort move interleaved {key, value} records -- one
+// 64-bit load and one 64-bit store per pair instead of two 32-bit ones, i.e. half the global-memory instructions and
+// ~2 fewer L1 wavefronts per 32 pairs: 1 = separate in, interleaved out (pass 0); 2 = interleaved both (passes 1, 2);
+// 3 = interleaved in, separate out (pass 3). Interleaved arrays travel through keys_in / keys_out (as uint2*).
+template <typename Cfg, typename StatusT, bool kHasValues, bool kPeer = false, typename KeyT = uint32_t, int kIO = 0>
 __global__ void __launch_bounds__(Cfg::kBlock, Cfg::kCtasPerSM)
 k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ digit_base /* [256] */,
@@ -207,9 +262,13 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
     using SM = PassSmem<Cfg, kHasValues, (int)sizeof(KeyT)>;
     constexpr bool kWide = sizeof(KeyT) == 8;
     static_assert(!(kWide && kPeer), "the multi-GPU bucket exchange is built for 32-bit keys");
+    constexpr bool kInPairs = kIO == 2 || kIO == 3, kOutPairs = kIO == 1 || kIO == 2;
+    static_assert(kIO == 0 || (kHasValues && !kWide && !kPeer), "interleaved records: 32-bit keys with values");
     constexpr int kBlock = Cfg::kBlock, kIPT = Cfg::kIPT, kTile = Cfg::kTile, kWarps = Cfg::kWarps;
-    constexpr int kGroups = 2 * kWarps, kH = SM::kH, kGP = kGroups / kH;      // groups per scan thread
-    static_assert(kIPT % 4 == 0 && 16 * kIPT <= 256, "ranks are packed four to a register (< 256 each)");
+    constexpr int kGroups = kGroupsPerWarp * kWarps, kH = SM::kH, kGP = kGroups / kH;      // groups per scan thread
+    constexpr int kLanes = 32 / kGroupsPerWarp;                                 // lanes per ranking group
+    constexpr int kPack = kFullWarpRank ? 3 : 4, kRankBits = 32 / kPack;        // ranks per register (10 / 8 bits each)
+    static_assert(kLanes * kIPT <= (1 << kRankBits), "packed ranks must fit their field");
     static_assert(kGroups % kH == 0, "scan threads split the groups evenly");
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* s_tbl = reinterpret_cast<uint32_t*>(smem);                         // [kGroups][256]
@@ -220,11 +279,23 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
     uint32_t* s_part = s_global_off + kRadix;                                    // [kH][256]
     uint32_t* s_scan = s_part + kH * kRadix;                                     // [kWarps]
     uint32_t* s_tile_id = s_scan + kWarps;
+    uint32_t* s_canary = s_tile_id + 4;                                          // [8]: lane-order self-test (see below)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     // dynamic tile id: a tile only ever waits on tiles that already started => forward progress
     if (tid == 0) *s_tile_id = atomicAdd(tile_counter, 1u);
+    if (kFullWarpRank && warp == 0) {
+        // Canary: the fast ranking below relies on one property of this SM's shared-memory atomic unit -- the lanes of
+        // ONE instruction that hit the same address are applied in ascending lane order. Test it here, on this SM,
+        // with a 32-way and four 8-way conflicts; if it ever fails this CTA ranks its tile the order-independent way.
+        if (lane < 8) s_canary[lane] = 0u;
+        __syncwarp();
+        const uint32_t a = atomicAdd(s_canary + 0, 1u);
+        const uint32_t b = atomicAdd(s_canary + 1 + (lane & 3u), 1u);
+        __syncwarp();
+        if (a != lane || b != (lane >> 2) || (flags & 1u)) s_canary[7] = 1u;
+    }
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
 #pragma unroll
@@ -235,47 +306,54 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
     const uint32_t tile_base = tile * (uint32_t)kTile;
     const uint32_t valid = min((uint32_t)kTile, n - tile_base);
 
-    // Group-major item map: 16-lane group G = 2*warp + lane/16 owns the 16*IPT consecutive keys from G*16*IPT,
-    // item i of lane l16 is key G*16*IPT + 16*i + l16 -- so (round, lane) order inside a group IS memory order,
-    // which is what makes the per-group ranks stable.
-    const uint32_t l16 = lane & 15u;
-    const uint32_t group = 2u * warp + (lane >> 4);
-    const uint32_t item0 = group * (16u * kIPT) + l16;
+    // Item map. A ranking group (a whole warp, or a 16-lane half in the fully verified flavour) owns kLanes * IPT
+    // CONSECUTIVE keys of the tile, item i of its lane l being key group * kLanes * IPT + kLanes * i + l -- so (round,
+    // lane) order inside a group IS memory order, which is what makes the per-group ranks stable. With whole warps a
+    // load is one coalesced 128-byte line; with half-warp groups it touches two 64-byte segments.
+    const uint32_t gl = lane & (uint32_t)(kLanes - 1);                      // lane within its group
+    const uint32_t group = (uint32_t)kGroupsPerWarp * warp + (kGroupsPerWarp == 2 ? (lane >> 4) : 0u);
+    const uint32_t item0 = group * (uint32_t)(kLanes * kIPT) + gl;
     KeyT key[kIPT];
-#ifndef USRT_LAB_SHFL_LOADS
-    // direct form: every load touches two 64-byte segments, one per group (two L1 wavefronts instead of one)
+    uint32_t val[kHasValues ? kIPT : 1];
 #pragma unroll
     for (int i = 0; i < kIPT; ++i) {
-        const uint32_t idx = item0 + (uint32_t)i * 16u;
-        key[i] = idx < valid ? __ldg(keys_in + tile_base + idx) : ~(KeyT)0;      // tail pads sort last, never stored
-    }
-#else
-    // (measured slower, 0.348 vs 0.334 ms per pass at 2^26: the shuffles cost more than the extra load wavefronts)
-    // Warp-striped 128-byte loads over the warp's 32*IPT keys, then one lane-xor-16 shuffle per pair of loads hands
-    // each half-warp the half of the chunk it owns: load i < IPT/2 holds group A's items 2i (lanes 0-15) and 2i+1
-    // (lanes 16-31); load i + IPT/2 holds group B's items 2i and 2i+1 the same way.
-    const bool upper = (lane & 16u) != 0u;
-    const uint32_t warp_first = warp * (32u * kIPT) + lane;
-    auto load_items = [&](const uint32_t* __restrict__ src, uint32_t (&item)[kIPT], uint32_t pad) {
-#pragma unroll
-        for (int i = 0; i < kIPT / 2; ++i) {
-            const uint32_t ia = warp_first + (uint32_t)i * 32u, ib = ia + 16u * kIPT;
-            const uint32_t a = ia < valid ? __ldg(src + tile_base + ia) : pad;
-            const uint32_t b = ib < valid ? __ldg(src + tile_base + ib) : pad;
-            const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, upper ? a : b, 16);
-            item[2 * i] = upper ? got : a;
-            item[2 * i + 1] = upper ? b : got;
+        const uint32_t idx = item0 + (uint32_t)i * kLanes;
+        if constexpr (kInPairs) {
+            const uint2 kv = idx < valid ? __ldg(reinterpret_cast<const uint2*>(keys_in) + tile_base + idx) : make_uint2(0xFFFFFFFFu, 0u);
+            key[i] = kv.x; val[i] = kv.y;
+        } else {
+            key[i] = idx < valid ? __ldg(keys_in + tile_base + idx) : ~(KeyT)0;  // tail pads sort last, never stored
         }
-    };
-    load_items(keys_in, key, 0xFFFFFFFFu);                   // tail pads sort last, never stored
-#endif
+    }
 
-    // stable rank of every key among the keys of its group with the same digit (< 256: four per register)
-    uint32_t rank4[kIPT / 4];
+    // stable rank of every key among the keys of its group with the same digit, kPack to a register
+    uint32_t rankp[(kIPT + kPack - 1) / kPack];
     uint32_t* tbl = s_tbl + group * kRadix;
-    {
-        const uint32_t add = (0x10000u << l16) | 1u, bit = 0x10000u << l16;
-        const uint32_t not_below = 0xFFFFu << l16;             // my own lane and the higher ones of my group
+    auto put_rank = [&](int i, uint32_t r) {
+        if (i % kPack == 0) rankp[i / kPack] = r; else rankp[i / kPack] |= r << ((i % kPack) * kRankBits);
+    };
+    if constexpr (kFullWarpRank) {
+        if (s_canary[7] == 0u) {
+            // One returning atomic per key: old = keys of this digit in the warp's earlier rounds + the lower lanes of this
+            // round (ascending-lane serialisation, validated by the canary above) = the stable rank.
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) {
+                put_rank(i, atomicAdd(tbl + ((uint32_t)(key[i] >> shift) & 255u), 1u));
+                __syncwarp();                                   // rounds are ordered
+            }
+        } else {
+            uint16_t* s_rank = reinterpret_cast<uint16_t*>(smem + SM::kTblBytes);       // the staging area is still free
+            const KeyT* tile_keys = kInPairs ? reinterpret_cast<const KeyT*>(reinterpret_cast<const uint2*>(keys_in) + tile_base)
+                                             : keys_in + tile_base;
+            rank_warp_order_independent<KeyT, kInPairs>(tile_keys, valid, item0, kIPT, shift, tbl, s_rank);
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) put_rank(i, s_rank[item0 + (uint32_t)i * kLanes]);
+        }
+    } else {
+        // Fully verified flavour: the word also carries the lane bits of the round, so a lane sees which lanes of its group
+        // were applied before it; a higher lane among them sends the warp to the order-independent method.
+        const uint32_t add = (0x10000u << gl) | 1u, bit = 0x10000u << gl;
+        const uint32_t not_below = 0xFFFFu << gl;              // my own lane and the higher ones of my group
         uint32_t out_of_order = flags & 1u;
 #pragma unroll
         for (int i = 0; i < kIPT; ++i) {
@@ -283,12 +361,9 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
             const uint32_t old = atomicAdd(tbl + d, add);
             __syncwarp();
             atomicSub(tbl + d, bit);
-#ifndef USRT_LAB_NO_SYNC2
             __syncwarp();
-#endif
             out_of_order |= (old >> 16) & not_below;
-            const uint32_t r = old & 0xFFFFu;
-            if ((i & 3) == 0) rank4[i >> 2] = r; else rank4[i >> 2] |= r << ((i & 3) * 8);
+            put_rank(i, old & 0xFFFFu);
         }
         if (__any_sync(0xFFFFFFFFu, out_of_order != 0u)) {
             // Order-independent ranking (never taken on B200 unless forced): start the warp's two tables over.
@@ -296,7 +371,7 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
 #pragma unroll
             for (int i = 0; i < 2 * kRadix / 32; ++i) mine[lane + 32 * i] = 0u;
             __syncwarp();
-            const uint32_t below = (1u << l16) - 1u;
+            const uint32_t below = (1u << gl) - 1u;
 #pragma unroll
             for (int i = 0; i < kIPT; ++i) {
                 const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
@@ -308,25 +383,19 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
                 const uint32_t before = __popc(peers & below);
                 if (before == 0) tbl[d] = total;                // the lowest peer clears the round's lane bits
                 __syncwarp();
-                const uint32_t r = total - __popc(peers) + before;
-                if ((i & 3) == 0) rank4[i >> 2] = r; else rank4[i >> 2] |= r << ((i & 3) * 8);
+                put_rank(i, total - __popc(peers) + before);
             }
         }
     }
     __syncthreads();
 
     // values are fetched now, so their latency hides behind the scan and the look-back below
-    uint32_t val[kHasValues ? kIPT : 1];
-    if (kHasValues) {
-#ifndef USRT_LAB_SHFL_LOADS
+    if (kHasValues && !kInPairs) {
 #pragma unroll
         for (int i = 0; i < kIPT; ++i) {
-            const uint32_t idx = item0 + (uint32_t)i * 16u;
+            const uint32_t idx = item0 + (uint32_t)i * kLanes;
             val[i] = idx < valid ? __ldg(vals_in + tile_base + idx) : 0u;
         }
-#else
-        load_items(vals_in, reinterpret_cast<uint32_t (&)[kIPT]>(val), 0u);
-#endif
     }
 
     // Scan step: kH threads per digit, each owning kGP consecutive groups. Thread (d, h) sums its groups' counts of
@@ -381,7 +450,7 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
 #pragma unroll
     for (int i = 0; i < kIPT; ++i) {
         const uint32_t dg = (uint32_t)(key[i] >> shift) & 255u;
-        const uint32_t slot = tbl[dg] + ((rank4[i >> 2] >> ((i & 3) * 8)) & 0xFFu);
+        const uint32_t slot = tbl[dg] + ((rankp[i / kPack] >> ((i % kPack) * kRankBits)) & ((1u << kRankBits) - 1u));
         if constexpr (kHasValues && !kWide) {
             s_pairs[slot] = make_uint2((uint32_t)key[i], val[i]);
         } else {
@@ -392,26 +461,26 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
     // Look-back AFTER staging: the aggregate was published before the scan, so by now the preceding
     // tiles have usually posted their inclusive prefixes and the walk resolves in one round trip.
     if (h == 0) {
-        // decoupled look-back over the preceding tiles' counts of this digit, four tiles per round
+        // decoupled look-back over the preceding tiles' counts of this digit, kLookBack tiles per round
         // trip (the loads are independent; only the accumulation is ordered)
         uint32_t exclusive = 0;
         if (tile > 0) {
             int32_t t = (int32_t)tile - 1;
             bool done = false;
             while (!done) {
-                StatusT s4[4];
+                StatusT sw[kLookBack];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    s4[k] = (t - k >= 0) ? ST::load(status + (size_t)(t - k) * kRadix + d) : (StatusT)ST::kPrefix;
+                for (int k = 0; k < kLookBack; ++k)
+                    sw[k] = (t - k >= 0) ? ST::load(status + (size_t)(t - k) * kRadix + d) : (StatusT)ST::kPrefix;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < kLookBack; ++k) {
                     if (!done) {
-                        while ((s4[k] & ST::kFlagMask) == 0) s4[k] = ST::load(status + (size_t)(t - k) * kRadix + d);
-                        exclusive += (uint32_t)(s4[k] & ST::kValueMask);
-                        done = (s4[k] & ST::kPrefix) != 0;
+                        while ((sw[k] & ST::kFlagMask) == 0) sw[k] = ST::load(status + (size_t)(t - k) * kRadix + d);
+                        exclusive += (uint32_t)(sw[k] & ST::kValueMask);
+                        done = (sw[k] & ST::kPrefix) != 0;
                     }
                 }
-                t -= 4;
+                t -= kLookBack;
             }
             ST::store(my_status, ST::kPrefix | (StatusT)(exclusive + count));
         }
@@ -434,6 +503,8 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
                         reinterpret_cast<uint32_t*>(kp)[dst] = kv.x;
                         reinterpret_cast<uint32_t*>(vp)[dst] = kv.y;
                     }
+                } else if (kOutPairs) {
+                    reinterpret_cast<uint2*>(keys_out)[dst] = kv;
                 } else {
                     keys_out[dst] = kv.x;
                     vals_out[dst] = kv.y;
@@ -542,20 +613,25 @@ inline uint32_t pass_flags() {
 }
 inline uint64_t status_words_bytes(uint64_t count) { return (uint64_t)num_tiles(count) * kRadix * (wide_status(count) ? 8 : 4); }
 
-template <typename Cfg, typename StatusT, bool kHasValues>
+template <typename Cfg, typename StatusT, bool kHasValues, int kIO = 0>
 cudaError_t launch_pass(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint64_t count, int shift,
                         const uint32_t* digit_base, uint32_t* tile_counter, void* status, cudaStream_t stream) {
     constexpr int smem = PassSmem<Cfg, kHasValues>::kTotal;
-    cudaFuncSetAttribute(k_onesweep<Cfg, StatusT, kHasValues>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    k_onesweep<Cfg, StatusT, kHasValues><<<num_tiles(count), Cfg::kBlock, smem, stream>>>(
-        ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter, static_cast<StatusT*>(status), pass_flags());
+    auto kern = k_onesweep<Cfg, StatusT, kHasValues, false, uint32_t, kIO>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<num_tiles(count), Cfg::kBlock, smem, stream>>>(ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter,
+                                                         static_cast<StatusT*>(status), pass_flags(), nullptr, nullptr);
     return cudaGetLastError();
 }
 
+// io: 0 separate arrays; 1 / 2 / 3 interleaved records out / both / in (big tiles with values only)
 template <typename StatusT>
 cudaError_t run_pass(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint64_t count, int shift,
-                     const uint32_t* digit_base, uint32_t* tile_counter, void* status, cudaStream_t stream) {
+                     const uint32_t* digit_base, uint32_t* tile_counter, void* status, cudaStream_t stream, int io = 0) {
     const bool small = count < kSmallSortLimit;
+    if (io == 1) return launch_pass<BigTile, StatusT, true, 1>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
+    if (io == 2) return launch_pass<BigTile, StatusT, true, 2>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
+    if (io == 3) return launch_pass<BigTile, StatusT, true, 3>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
     if (vi != nullptr)
         return small ? launch_pass<SmallTile, StatusT, true>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream)
                      : launch_pass<BigTile, StatusT, true>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
@@ -579,6 +655,21 @@ cudaError_t sort_scratch_reserve(SortScratch& s, uint64_t count, bool need_alt) 
         s.status_bytes = need;
         ++s.generation;
     }
+    // two interleaved {key, value} buffers for the intermediate passes of large sorts (best effort: a sort that cannot
+    // get them runs all four passes on separate arrays)
+    if (count >= kPairsSortLimit && count > s.pairs_capacity && getenv("USRT_SORT_NO_PAIRS") == nullptr) {
+        if (s.pairs_x) cudaFree(s.pairs_x);
+        if (s.pairs_y) cudaFree(s.pairs_y);
+        s.pairs_x = s.pairs_y = nullptr; s.pairs_capacity = 0;
+        if (cudaMalloc(&s.pairs_x, count * 8) == cudaSuccess && cudaMalloc(&s.pairs_y, count * 8) == cudaSuccess) {
+            s.pairs_capacity = count;
+        } else {
+            cudaGetLastError();
+            if (s.pairs_x) cudaFree(s.pairs_x);
+            s.pairs_x = s.pairs_y = nullptr;
+        }
+        ++s.generation;
+    }
     if (need_alt && count > s.alt_capacity) {
         if (s.keys_alt) cudaFree(s.keys_alt);
         if (s.vals_alt) cudaFree(s.vals_alt);
@@ -597,6 +688,8 @@ void sort_scratch_free(SortScratch& s) {
     if (s.vals_alt) cudaFree(s.vals_alt);
     if (s.keys64_alt) cudaFree(s.keys64_alt);
     if (s.vals64_alt) cudaFree(s.vals64_alt);
+    if (s.pairs_x) cudaFree(s.pairs_x);
+    if (s.pairs_y) cudaFree(s.pairs_y);
     s = SortScratch();
 }
 
@@ -620,18 +713,31 @@ cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint3
     char* status0 = static_cast<char*>(s.status) + kHeaderWords * 4;
     const uint32_t* ki = keys; const uint32_t* vi = vals;
     uint32_t* ko = keys_alt; uint32_t* vo = vals_alt;
+    // large key/value sorts: (keys, vals) -> X -> Y -> X -> (keys, vals) with X, Y interleaved {key, value} records
+    const bool pairs = vals != nullptr && count >= kPairsSortLimit && s.pairs_capacity >= count && count >= kSmallSortLimit;
     for (int pass = 0; pass < kSortPasses; ++pass) {               // bitOffset = 0, 8, 16, 24
         void* st = status0 + (uint64_t)pass * pass_bytes;
+        int io = 0;
+        if (pairs) {
+            uint32_t* x = reinterpret_cast<uint32_t*>(s.pairs_x); uint32_t* y = reinterpret_cast<uint32_t*>(s.pairs_y);
+            io = pass == 0 ? 1 : (pass == kSortPasses - 1 ? 3 : 2);
+            ki = pass == 0 ? keys : (pass == 2 ? y : x);           // passes 1 and 3 read X, pass 2 reads Y
+            vi = vals;
+            ko = pass == kSortPasses - 1 ? keys : (pass == 1 ? y : x);
+            vo = vals;
+        }
         if (wide_status(count))
-            e = run_pass<uint64_t>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream);
+            e = run_pass<uint64_t>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream, io);
         else
-            e = run_pass<uint32_t>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream);
+            e = run_pass<uint32_t>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream, io);
         if (e != cudaSuccess) return e;
         if (launches) *launches += 1;
         if (events && (e = cudaEventRecord(events[2 + pass], stream)) != cudaSuccess) return e;
-        const uint32_t* tk = ki; const uint32_t* tv = vi;
-        ki = ko; vi = vo;
-        ko = const_cast<uint32_t*>(tk); vo = const_cast<uint32_t*>(tv);
+        if (!pairs) {
+            const uint32_t* tk = ki; const uint32_t* tv = vi;
+            ki = ko; vi = vo;
+            ko = const_cast<uint32_t*>(tk); vo = const_cast<uint32_t*>(tv);
+        }
     }
     return cudaSuccess;   // even number of passes: the result is back in (keys, vals)
 }

@@ -24,6 +24,9 @@ struct SortScratch {
     uint32_t* keys_alt = nullptr;      // ping-pong partners for the standalone sorter
     uint32_t* vals_alt = nullptr;
     uint64_t alt_capacity = 0;         // elements
+    uint2* pairs_x = nullptr;          // interleaved {key, value} records of the intermediate passes of large sorts
+    uint2* pairs_y = nullptr;
+    uint64_t pairs_capacity = 0;
     uint64_t* keys64_alt = nullptr;    // the same for the 64-bit-key sorter
     uint32_t* vals64_alt = nullptr;
     uint64_t alt64_capacity = 0;
