@@ -14,6 +14,9 @@
 #          semantics; `1e-8`, `0.5`, `0.4` -> `1e-8f` ... (an HLSL literal is fp32; a C++ one would be a double);
 #          `.xyz` / `.xy` swizzles -> `.xyz()` / `.xy()`; one hook line `USRT_REF_HIT(id, result);` ahead of
 #          Raytracing.compute:178 so the hit record can be read out (the reference never stores it).
+#          Sorting/*.compute additionally run under a lock-step wave emulator (oracle/ref_shim/wave_emulator.hpp): every
+#          thread of a 1024-thread group is a coroutine, group barriers and WavePrefixCountBits / WavePrefixSum block
+#          until their participants have arrived.
 #   C#   : `private static`/`public` dropped, `out T x` -> `T& x`, `new T(` -> `T(`, `Math.` -> `Math::`,
 #          `new AABB { min = min, max = max }` -> `AABB { .min = min, .max = max }`.
 set -euo pipefail
@@ -36,6 +39,11 @@ hlsl "$SHADERS/Raytracing/Raytracing.compute" \
     > "$OUT/gen_Raytracing.inc"
 grep -q 'USRT_REF_HIT' "$OUT/gen_Raytracing.inc" || { echo "build_ref.sh: hook line not placed" >&2; exit 4; }
 
+# the five sort kernels (run under oracle/ref_shim/wave_emulator.hpp)
+for f in LocalRadixSort Scan GlobalRadixSort; do
+    hlsl "$SHADERS/Sorting/$f.compute" > "$OUT/gen_$f.inc"
+done
+
 # MeshBufferContainer.cs: ExpandBits .. NormalizeCentroid (:32-83) and DistributeKeys (:154-169)
 CS="$REF/Assets/_Scripts/MeshBufferContainer.cs"
 sed -n '32,83p;154,169p' "$CS" \
@@ -49,8 +57,8 @@ grep -q 'static uint ExpandBits' "$OUT/gen_MeshBufferContainer.inc" && grep -q '
 CXX="${CXX:-g++}"
 # same arithmetic flags as the oracle: IEEE fp32 per operation, no contraction, no fast-math, no -march
 FLAGS="-O2 -std=c++20 -ffp-contract=off -fno-fast-math -fPIC -pthread -Wno-narrowing -Wno-unknown-pragmas -w -I$REF -I$HERE/ref_shim"
-for tu in ref_mesh ref_bvh ref_raytracing; do
+for tu in ref_mesh ref_bvh ref_raytracing ref_sort; do
     $CXX $FLAGS -c "$HERE/ref_shim/$tu.cpp" -o "$OUT/$tu.o"
 done
-$CXX -shared -pthread -o "$OUT/libusrt_ref.so" "$OUT/ref_mesh.o" "$OUT/ref_bvh.o" "$OUT/ref_raytracing.o"
+$CXX -shared -pthread -o "$OUT/libusrt_ref.so" "$OUT/ref_mesh.o" "$OUT/ref_bvh.o" "$OUT/ref_raytracing.o" "$OUT/ref_sort.o"
 echo "$OUT/libusrt_ref.so"

@@ -3,17 +3,18 @@
 // DistributeKeys -> Karras LBVH topology -> atomic-counter bottom-up AABB refit -> 64-entry
 // stack traversal with the reference's slab and Moller-Trumbore tests.
 //
-// PINNED AGAINST THE REFERENCE'S OWN TEXT (round 2): oracle/build_ref.sh compiles BVH.compute, Raytracing.compute and
-// the static functions + DistributeKeys of MeshBufferContainer.cs with g++ (oracle/_ref/libusrt_ref.so, a syntactic
-// sed pass + shim headers for the HLSL / UnityEngine types); tests/test_ref_pin.py requires this file to agree with it
-// bit for bit on every build buffer, on full primary frames (configs[0] 512x512, configs[1] 1920x1080 at 1,048,576
-// triangles via tests/golden/ref_digests.json) and on the shading epilogue. NOT pinned that way: the Sorting/*.compute
-// kernels (wave intrinsics + group barriers; see tests/test_ref_sort.py if present) -- the sort is pinned by its
-// contract, a stable ascending sort by the 32-bit key (ComputeBufferSorter.cs:150-177), the reference's per-pass
-// validators and std::stable_sort; the reference ships no golden vectors of its own.
-// The arithmetic the HLSL leaves to the hardware (normalize -> rsqrt, 1/x -> rcp, FMA contraction) is DEFINED here as
-// IEEE fp32 per-operation, left-to-right, no contraction (build with -ffp-contract=off, no fast-math); the shim headers
-// of the _ref build carry the same definitions and nothing else.
+// PINNED AGAINST THE REFERENCE'S OWN TEXT (round 2): oracle/build_ref.sh compiles BVH.compute, Raytracing.compute, the
+// five Sorting/*.compute kernels and the static functions + DistributeKeys of MeshBufferContainer.cs with g++
+// (oracle/_ref/libusrt_ref.so: a syntactic sed pass, shim headers for the HLSL / UnityEngine types, and a lock-step wave
+// emulator -- coroutines per thread, group barriers, WavePrefixCountBits / WavePrefixSum -- for the sort kernels).
+// tests/test_ref_pin.py requires this file to agree with it bit for bit: every build buffer, every intermediate of a
+// sort pass (block-sorted pairs, per-block digit offsets, the count table before / after the scan) incl. one pass at the
+// reference's full 512 x 1024 capacity, full primary frames (configs[0] 512x512; configs[1] 1920x1080 at 1,048,576
+// triangles via tests/golden/ref_digests.json) and the shading epilogue. The reference ships no golden vectors of its
+// own; its runtime self-checks are restated in tests/test_oracle.py.
+// The arithmetic the HLSL leaves to the hardware (normalize -> rsqrt, 1/x -> rcp, FMA contraction, the bilinear sampler)
+// is DEFINED here as IEEE fp32 per-operation, left-to-right, no contraction (build with -ffp-contract=off, no
+// fast-math); the shim headers of the _ref build carry the same definitions and nothing else.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library. The product (unitysimpleraytracing_b200/) never does.

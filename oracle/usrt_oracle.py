@@ -2,9 +2,9 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
 this module. Pinned against the reference's own text compiled by oracle/build_ref.sh (oracle/_ref,
-tests/test_ref_pin.py) for Morton/AABB, DistributeKeys, tree, refit, traversal and shading; the sort
-is pinned by its contract (stable sort), the reference's runtime self-checks, an independent numpy
-restatement (np_oracle.py) and brute-force cross-checks. See the header of usrt_oracle.cpp.
+tests/test_ref_pin.py) for Morton/AABB, the sort (all five kernels under a wave emulator), DistributeKeys,
+tree, refit, traversal and shading; further cross-checked by the reference's runtime self-checks, an
+independent numpy restatement (np_oracle.py) and brute force. See the header of usrt_oracle.cpp.
 
 The struct dtypes are declared here independently of the product package on purpose, so that a
 layout bug in the product's header shows up as a byte mismatch in the parity tests.

@@ -1,7 +1,8 @@
 """ctypes loader for oracle/_ref/libusrt_ref.so -- TEST INFRASTRUCTURE ONLY.
 
-That library is the REFERENCE'S OWN TEXT (BVH.compute, Raytracing.compute, the static functions and DistributeKeys of
-MeshBufferContainer.cs), compiled with g++ through the syntactic recipe in oracle/build_ref.sh. It pins the
+That library is the REFERENCE'S OWN TEXT (BVH.compute, Raytracing.compute, Sorting/*.compute, the static functions and
+DistributeKeys of MeshBufferContainer.cs), compiled with g++ through the syntactic recipe in oracle/build_ref.sh; the
+sort kernels run under a lock-step wave emulator (oracle/ref_shim/wave_emulator.hpp). It pins the
 hand-written restatement oracle/usrt_oracle.cpp (tests/test_ref_pin.py) and generates the golden digests under
 tests/golden/ (tests/golden/make_ref_golden.py). /root/reference exists only in the build container: on the GPU box the
 prebuilt .so is used if it travelled with the snapshot, and nothing here is imported by the product.
@@ -107,17 +108,24 @@ def raytracing(sorted_indices, tri_aabb, internal, leaf, bvh, tris, width, heigh
 
 
 class Scene:
-    """RaytracingMeshDrawer.Awake() (:30-54) with the reference's own code for every stage it has as C-like text.
-    The radix sort (Sorting/*.compute, wave intrinsics + group barriers) is not part of this library; its contract --
-    a stable ascending sort by the 32-bit key (ComputeBufferSorter.cs:150-177) -- is applied with numpy."""
+    """RaytracingMeshDrawer.Awake() (:30-54) with the reference's own code for every stage: MeshBufferContainer's Morton /
+    AABB functions, the five Sorting kernels under the wave emulator, DistributeKeys, TreeConstructor, BVHConstructor.
+    The sort kernels are hard-wired to 512 blocks of 1024 elements (Scan.compute:50,64); meshes beyond that capacity
+    (BASELINE configs[1] and up) take the sort's contract instead -- a stable ascending sort by the 32-bit key
+    (ComputeBufferSorter.cs:150-177) -- applied with numpy, and say so in `sorted_by`."""
 
     def __init__(self, tris):
         self.triangleData = np.ascontiguousarray(tris, TRIANGLE)
         self.n = n = len(tris)
         self.mortonCodes, idx, self.triangleAABB = morton(self.triangleData)
-        order = np.argsort(self.mortonCodes, kind="stable")
-        self.sortedMortonRaw = self.mortonCodes[order]
-        self.sortedTriangleIndices = idx[order]
+        if n <= REF_BLOCKS * 1024:
+            self.sortedMortonRaw, self.sortedTriangleIndices = sort(self.mortonCodes, idx)
+            self.sorted_by = "reference kernels (Sorting/*.compute under the wave emulator)"
+        else:
+            order = np.argsort(self.mortonCodes, kind="stable")
+            self.sortedMortonRaw = self.mortonCodes[order]
+            self.sortedTriangleIndices = idx[order]
+            self.sorted_by = "numpy stable sort (mesh exceeds the reference's fixed 524,288-element sort capacity)"
         self.sortedMortonCodes = distribute_keys(self.sortedMortonRaw)
         self.internalNodes, self.leafNodes = construct_tree(self.sortedMortonCodes, n)
         self.bvhData = construct_bvh(n, self.sortedTriangleIndices, self.triangleAABB, self.internalNodes, self.leafNodes)
@@ -125,3 +133,35 @@ class Scene:
     def trace_primary(self, width, height, near, tan_half_fov, cam_to_world, texture=None, threads=None):
         return raytracing(self.sortedTriangleIndices, self.triangleAABB, self.internalNodes, self.leafNodes, self.bvhData,
                           self.triangleData, width, height, near, tan_half_fov, cam_to_world, texture, threads)
+
+
+# ---- the reference's five sort kernels under the lock-step wave emulator (oracle/ref_shim/wave_emulator.hpp) ----------
+REF_BLOCKS = 512          # Constants.cginc:3 BLOCK_SIZE: the count tables are laid out for 512 blocks whatever is dispatched
+
+
+def sort_pass(keys, values, bit_offset):
+    """One pass of ComputeBufferSorter.Sort() (:104-116) through LocalRadixSort, PreScan, BlockSum, GlobalScan and
+    GlobalRadixSort as written. len(keys) must be a multiple of 1024 and at most 512 * 1024. Returns every
+    intermediate in the reference's layouts: offsets[block * 256 + digit], sizes[digit * 512 + block]."""
+    n = len(keys)
+    assert n % 1024 == 0 and 0 < n <= REF_BLOCKS * 1024
+    k = np.array(keys, np.uint32); v = np.array(values, np.uint32)
+    out = dict(sortedBlocksKeys=np.empty(n, np.uint32), sortedBlocksValues=np.empty(n, np.uint32),
+               offsets=np.zeros(REF_BLOCKS * 256, np.uint32), sizesBefore=np.zeros(REF_BLOCKS * 256, np.uint32),
+               sizesAfter=np.zeros(REF_BLOCKS * 256, np.uint32))
+    lib().usrt_ref_sort_pass(_p(k), _p(v), ctypes.c_int(n // 1024), ctypes.c_int(bit_offset), _p(out["sortedBlocksKeys"]),
+                             _p(out["sortedBlocksValues"]), _p(out["offsets"]), _p(out["sizesBefore"]), _p(out["sizesAfter"]))
+    out["keys"] = k; out["values"] = v
+    return out
+
+
+def sort(keys, values):
+    """ComputeBufferSorter.Sort() (:100-126): four passes of the kernels above. Padded like the reference's buffers
+    (MeshBufferContainer.cs:108-109: unused slots hold 0xFFFFFFFF, which sink to the end) and cut back to len(keys)."""
+    n = len(keys)
+    padded = -(-n // 1024) * 1024
+    assert padded <= REF_BLOCKS * 1024
+    k = np.full(padded, 0xFFFFFFFF, np.uint32); v = np.full(padded, 0xFFFFFFFF, np.uint32)
+    k[:n] = keys; v[:n] = values
+    lib().usrt_ref_sort(_p(k), _p(v), ctypes.c_int(padded // 1024))
+    return k[:n].copy(), v[:n].copy()

@@ -6,9 +6,10 @@ BVH.compute, Raytracing.compute and MeshBufferContainer.cs compiled by oracle/bu
 sha256 of every buffer the build produces and of full primary frames, for the BASELINE configurations the oracle can
 be checked on in seconds: the reference's own scene mesh (12,800 triangles), configs[0] (65,536-triangle soup, 512x512
 rays) and configs[1] at FULL size (1,048,576 triangles, 1920x1080 rays). The GPU parity tests and bench.py compare
-the CUDA path with these digests on the GPU box, where /root/reference does not exist. The Sorting/*.compute kernels
-are not in libusrt_ref.so; the sorted arrays digested here are the stable sort of the reference-computed keys, which
-is the contract ComputeBufferSorter.ValidateSortedData checks (ComputeBufferSorter.cs:150-177).
+the CUDA path with these digests on the GPU box, where /root/reference does not exist. The first two cases are sorted by the reference's own
+Sorting/*.compute kernels (under the wave emulator); configs[1] exceeds their hard-wired 524,288-element capacity
+(Scan.compute:50,64), so its sorted arrays are the stable sort of the reference-computed keys -- the contract
+ComputeBufferSorter.ValidateSortedData checks (ComputeBufferSorter.cs:150-177). `sorted_by` records which.
 """
 import hashlib
 import json
@@ -55,6 +56,7 @@ def main():
         d["primary_%dx%d" % (w, h)] = sha(hits)
         d["primary_hit_count"] = int((hits["distance"] != np.float32(2139095040.0)).sum())
         d["n"] = int(s.n)
+        d["sorted_by"] = s.sorted_by
         out[name] = d
         print("%s: n=%d frame %dx%d hits=%d (%.1f s)" % (name, s.n, w, h, d["primary_hit_count"], time.time() - t0))
     with open(os.path.join(HERE, "ref_digests.json"), "w") as f:

@@ -342,3 +342,59 @@ def test_fitted_world_box_opt_in(oracle):
         s = oracle.Scene(tris, lo, hi)
         assert s.count_corrupted() == (0, 0) if hasattr(s, "count_corrupted") else True
         assert np.array_equal(np.sort(s.sortedTriangleIndices), np.arange(len(tris)))
+
+
+# ---- SURVEY 8(f)-4 key variants: the oracle twins are self-consistent -------------------------------------------------
+@pytest.mark.parametrize("kind", ["uniform", "few", "low32", "high32"])
+def test_sort64_twin_equals_stable_sort(oracle, kind):
+    rng = np.random.default_rng(len(kind))
+    k = rng.integers(0, 2 ** 64, 50000, dtype=np.uint64)
+    if kind == "few":
+        k = (k % 19) << np.uint64(37)
+    elif kind == "low32":
+        k &= np.uint64(0xFFFFFFFF)
+    elif kind == "high32":
+        k &= np.uint64(0xFFFFFFFF00000000)
+    v = np.arange(len(k), dtype=np.uint32)
+    a, b = oracle.sort64(k, v), oracle.stable_sort64(k, v)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    order = np.argsort(k, kind="stable")
+    assert np.array_equal(a[1], order.astype(np.uint32))
+
+
+def test_distribute_keys64_twin(oracle):
+    k = np.sort(np.random.default_rng(5).integers(0, 2 ** 63, 4000, dtype=np.uint64))
+    k[100:140] = k[100]                                              # a run of equal keys
+    d = oracle.distribute_keys64(k)
+    assert d[0] == 0 and (np.diff(d.astype(np.int64)) > 0).all()
+    want = np.concatenate([[0], np.cumsum(np.maximum(np.diff(k.astype(object)), 1))]).astype(object)
+    assert [int(x) for x in d] == [int(x) % 2 ** 64 for x in want]
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mesh", ["grid", "soup", "identical"])
+def test_variant_trees_are_valid_and_trace_like_brute_force(oracle, mode, mesh):
+    """Index tie-break (mode 1) and 63-bit Morton keys (mode 2): every node written once, parent/child reciprocity, the
+    in-order leaves are 0..n-1, node boxes contain their subtree, and the walk equals brute force in visiting order."""
+    tris = {"grid": meshes.reference_scene_grid(), "soup": meshes.uniform_soup(3000, seed=8),
+            "identical": np.repeat(meshes.uniform_soup(1, seed=45), 700)}[mesh]
+    s = oracle.VariantScene(tris, mode)
+    n = s.n
+    I, L = s.internalNodes[:n - 1], s.leafNodes
+    assert not (L["parent"] == 0xFFFFFFFF).any() and (L["index"] == np.arange(n)).all()
+    assert (I["index"] == np.arange(n - 1)).all() and I["parent"][0] == 0xFFFFFFFF
+    for side in ("left", "right"):
+        c, t = I[side + "Node"], I[side + "NodeType"]
+        assert (L["parent"][c[t == 1]] == np.nonzero(t == 1)[0]).all()
+        inner = np.nonzero(t == 0)[0]
+        assert (I["parent"][c[inner]] == inner).all()
+    order = s.visit_order()
+    assert sorted(order.tolist()) == sorted(s.sortedTriangleIndices.tolist())
+    root = s.bvhData[0]
+    assert np.allclose(root["min"], s.triangleAABB["min"].min(0)) and np.allclose(root["max"], s.triangleAABB["max"].max(0))
+    extent = 4.0 if mesh == "grid" else 100.0
+    rays = meshes.incoherent_rays(400, seed=12, extent=extent)
+    assert s.trace_rays(rays).tobytes() == s.brute_force(rays, order=order).tobytes()
+    if mode == 1:
+        base = oracle.Scene(tris)
+        assert np.array_equal(s.sortedTriangleIndices, base.sortedTriangleIndices)       # same sort, different tree keys

@@ -120,3 +120,55 @@ def test_oracle_reproduces_reference_generated_digests(oracle):
         assert sha(s.bvhData[:n - 1]) == d[name]["bvhData"], name
         frame = s.trace_primary(w, h, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], threads=os.cpu_count() or 1)
         assert sha(frame) == d[name]["primary_%dx%d" % (w, h)], name
+
+
+# ---- the reference's five sort kernels, run as written under the lock-step wave emulator -----------------------------
+def _keys(kind, n, seed):
+    rng = np.random.default_rng(seed)
+    k = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    if kind == "morton30":
+        k >>= np.uint32(2)
+    elif kind == "few":
+        k = ((k % 7) << np.uint32(21)).astype(np.uint32)
+    elif kind == "equal":
+        k[:] = 0x12345678
+    elif kind == "padded":                    # real keys followed by the 0xFFFFFFFF padding of MeshBufferContainer.cs:108-109
+        k[n - n // 3:] = 0xFFFFFFFF
+    return k
+
+
+@pytest.mark.parametrize("kind", ["uniform", "morton30", "few", "equal", "padded"])
+@pytest.mark.parametrize("bit_offset", [0, 8, 16, 24])
+def test_sort_pass_intermediates_match_the_sort_kernels(oracle, ref, kind, bit_offset):
+    """LocalRadixSort -> PreScan / BlockSum / GlobalScan -> GlobalRadixSort: block-sorted keys / values, per-block digit
+    offsets, the digit-major count table before and after the scan, and the scattered output, all byte for byte."""
+    n = 8192
+    k = _keys(kind, n, 100 + bit_offset); v = np.arange(n, dtype=np.uint32)
+    r, o = ref.sort_pass(k, v, bit_offset), oracle.sort_pass(k, v, bit_offset)
+    nb = n // 1024
+    for f in ("sortedBlocksKeys", "sortedBlocksValues", "keys", "values"):
+        assert np.array_equal(r[f], o[f]), f
+    assert np.array_equal(r["offsets"][:nb * 256], o["offsets"])
+    # the reference lays the count table out for its fixed 512 blocks (sizes[digit * 512 + block]), the oracle for nb blocks
+    assert np.array_equal(r["sizesBefore"].reshape(256, 512)[:, :nb], o["sizesBefore"].reshape(256, nb))
+    assert np.array_equal(r["sizesAfter"].reshape(256, 512)[:, :nb], o["sizesAfter"].reshape(256, nb))
+    assert not r["sizesBefore"].reshape(256, 512)[:, nb:].any()
+
+
+@pytest.mark.parametrize("kind,n", [("uniform", 65536), ("morton30", 20000), ("few", 5000), ("equal", 3000), ("uniform", 1)])
+def test_full_sort_matches_the_sort_kernels(oracle, ref, kind, n):
+    k = _keys(kind, n, n); v = np.arange(n, dtype=np.uint32)
+    rk, rv = ref.sort(k, v)
+    ok, ov = oracle.sort(k, v)
+    assert np.array_equal(rk, ok) and np.array_equal(rv, ov)
+    assert np.array_equal(rv, np.argsort(k, kind="stable").astype(np.uint32))      # the net contract: a stable sort
+
+
+def test_one_pass_at_the_reference_capacity(oracle, ref):
+    """All 512 blocks x 1024 elements, the only size the reference itself ever runs (Constants.cs:3-6)."""
+    n = 512 * 1024
+    k = _keys("morton30", n, 7); k[400000:] = 0xFFFFFFFF                            # a 400,000-triangle mesh, padded
+    v = np.arange(n, dtype=np.uint32); v[400000:] = 0xFFFFFFFF
+    r, o = ref.sort_pass(k, v, 8), oracle.sort_pass(k, v, 8)
+    assert np.array_equal(r["keys"], o["keys"]) and np.array_equal(r["values"], o["values"])
+    assert np.array_equal(r["sizesAfter"].reshape(256, 512), o["sizesAfter"].reshape(256, 512))
