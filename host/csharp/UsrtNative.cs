@@ -38,6 +38,10 @@ namespace Usrt
         [DllImport(Lib)] public static extern int usrt_morton(IntPtr ctx);
         [DllImport(Lib)] public static extern int usrt_sort(IntPtr ctx);
         [DllImport(Lib)] public static extern int usrt_sort_pairs_host(IntPtr ctx, [In, Out] uint[] keys, [In, Out] uint[] values, ulong count);
+        [DllImport(Lib)] public static extern int usrt_sort_pairs64_host(IntPtr ctx, [In, Out] ulong[] keys, [In, Out] uint[] values, ulong count);   // ComputeBufferSorter<ulong, uint>
+        [DllImport(Lib)] public static extern int usrt_set_key_mode(IntPtr ctx, int mode);   // 0 reference, 1 index tie-break (no DistributeKeys), 2 63-bit Morton keys
+        [DllImport(Lib)] public static extern int usrt_upload_positions(IntPtr ctx, [In] float[] positions12PerTriangle, uint n);   // first 48 bytes of every Triangle
+        [DllImport(Lib)] public static extern int usrt_upload_positions_async(IntPtr ctx, IntPtr pinnedPositions, uint n);
         [DllImport(Lib)] public static extern int usrt_distribute_keys(IntPtr ctx);
         [DllImport(Lib)] public static extern int usrt_construct_tree(IntPtr ctx);
         [DllImport(Lib)] public static extern int usrt_construct_bvh(IntPtr ctx);

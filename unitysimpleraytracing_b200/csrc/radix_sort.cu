@@ -232,6 +232,10 @@ constexpr bool kFullWarpRank = USRT_RANK_TRUST_LANE_ORDER != 0;
 #define USRT_LOOKBACK_WINDOW 4
 #endif
 constexpr int kLookBack = USRT_LOOKBACK_WINDOW;   // predecessor status words in flight per look-back round trip
+#ifndef USRT_PREFETCH_AHEAD
+#define USRT_PREFETCH_AHEAD 148
+#endif
+constexpr int kPrefetchAhead = USRT_PREFETCH_AHEAD;   // tiles between a CTA's own tile and the one it asks L2 to fetch (0: off)
 constexpr int kGroupsPerWarp = kFullWarpRank ? 1 : 2;
 
 template <typename Cfg, bool kHasValues, int kKeyBytes = 4> struct PassSmem {
@@ -305,6 +309,25 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
     const uint32_t tile = *s_tile_id;
     const uint32_t tile_base = tile * (uint32_t)kTile;
     const uint32_t valid = min((uint32_t)kTile, n - tile_base);
+    if (kPrefetchAhead > 0) {
+        // Ask L2 for a tile a little further down the input (tiles are handed out in order, so some CTA will want it
+        // soon): its own loads then hit L2 instead of waiting on DRAM at the start of a CTA, where nothing else of that
+        // CTA can run. Any distance from 64 to 300 tiles measures the same: 0.277 -> 0.264 ms per 2^26-pair pass.
+        const uint64_t ahead = (uint64_t)tile_base + (uint64_t)kPrefetchAhead * kTile;
+        if (ahead + kTile <= n) {
+            if constexpr (kInPairs) {
+                const char* p = reinterpret_cast<const char*>(reinterpret_cast<const uint2*>(keys_in) + ahead);
+                for (uint32_t b = tid * 128u; b < (uint32_t)kTile * 8u; b += kBlock * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+            } else {
+                const char* p = reinterpret_cast<const char*>(keys_in + ahead);
+                for (uint32_t b = tid * 128u; b < (uint32_t)kTile * (uint32_t)sizeof(KeyT); b += kBlock * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+                if (kHasValues) {
+                    const char* q = reinterpret_cast<const char*>(vals_in + ahead);
+                    for (uint32_t b = tid * 128u; b < (uint32_t)kTile * 4u; b += kBlock * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + b));
+                }
+            }
+        }
+    }
 
     // Item map. A ranking group (a whole warp, or a 16-lane half in the fully verified flavour) owns kLanes * IPT
     // CONSECUTIVE keys of the tile, item i of its lane l being key group * kLanes * IPT + kLanes * i + l -- so (round,
