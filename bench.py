@@ -640,8 +640,8 @@ def run_ours(args):
             "sort": {"pairs": ns, "ms": s_ms, "mkeys_s": ns / (s_ms * 1e-3) / 1e6, "achieved_gbs": sort_gbs,
                      "frac_of_measured_peak": sort_gbs / peak_gbs, "frac_of_8tbs": sort_gbs / 8000.0,
                      "histogram_ms": statistics.median(hist_ms), "pass_ms": p_ms,
-                     "cub_calibration": "cub::DeviceRadixSort::SortPairs on the same box, 2^26 pairs: 1.962 ms "
-                                        "(tools/micro/cub_sort_calib.cu, profiles/r02_summary.md)"},
+                     "cub_calibration": "cub::DeviceRadixSort::SortPairs on the same box, 2^26 pairs: 1.950 ms "
+                                        "(tools/micro/cub_sort_calib.cu, profiles/r02_cub_calibration.txt)"},
             "roofline": {"kernel": "k_onesweep (one 8-bit radix pass over 2^26 key/value pairs)", "bound": "hbm",
                          "achieved": pass_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": pass_gbs / peak_gbs,
                          "traffic": traffic, "peak_source": peak_src,

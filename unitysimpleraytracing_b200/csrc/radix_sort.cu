@@ -260,7 +260,8 @@ template <typename Cfg, typename StatusT, bool kHasValues, bool kPeer = false, t
 __global__ void __launch_bounds__(Cfg::kBlock, Cfg::kCtasPerSM)
 k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ digit_base /* [256] */,
-           uint32_t* __restrict__ tile_counter, StatusT* __restrict__ status /* [tiles][256], zeroed */, uint32_t flags,
+           uint32_t* __restrict__ tile_counter, StatusT* __restrict__ status /* [tiles][256], zeroed */,
+           StatusT* __restrict__ next_status /* the next pass's [tiles][256], zeroed HERE (may be NULL) */, uint32_t flags,
            const unsigned long long* __restrict__ key_ptrs = nullptr, const unsigned long long* __restrict__ val_ptrs = nullptr) {
     using ST = StatusTraits<StatusT>;
     using SM = PassSmem<Cfg, kHasValues, (int)sizeof(KeyT)>;
@@ -309,6 +310,9 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
     const uint32_t tile = *s_tile_id;
     const uint32_t tile_base = tile * (uint32_t)kTile;
     const uint32_t valid = min((uint32_t)kTile, n - tile_base);
+    // every tile clears its row of the NEXT pass's look-back words (that pass starts after this kernel has finished):
+    // one 1 KB store per tile instead of a memset over all passes' status before the sort
+    if (next_status != nullptr && tid < kRadix) next_status[(size_t)tile * kRadix + tid] = 0;
     if (kPrefetchAhead > 0) {
         // Ask L2 for a tile a little further down the input (tiles are handed out in order, so some CTA will want it
         // soon): its own loads then hit L2 instead of waiting on DRAM at the start of a CTA, where nothing else of that
@@ -638,28 +642,28 @@ inline uint64_t status_words_bytes(uint64_t count) { return (uint64_t)num_tiles(
 
 template <typename Cfg, typename StatusT, bool kHasValues, int kIO = 0>
 cudaError_t launch_pass(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint64_t count, int shift,
-                        const uint32_t* digit_base, uint32_t* tile_counter, void* status, cudaStream_t stream) {
+                        const uint32_t* digit_base, uint32_t* tile_counter, void* status, void* next_status, cudaStream_t stream) {
     constexpr int smem = PassSmem<Cfg, kHasValues>::kTotal;
     auto kern = k_onesweep<Cfg, StatusT, kHasValues, false, uint32_t, kIO>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     kern<<<num_tiles(count), Cfg::kBlock, smem, stream>>>(ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter,
-                                                         static_cast<StatusT*>(status), pass_flags(), nullptr, nullptr);
+                                                         static_cast<StatusT*>(status), static_cast<StatusT*>(next_status), pass_flags(), nullptr, nullptr);
     return cudaGetLastError();
 }
 
 // io: 0 separate arrays; 1 / 2 / 3 interleaved records out / both / in (big tiles with values only)
 template <typename StatusT>
 cudaError_t run_pass(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint64_t count, int shift,
-                     const uint32_t* digit_base, uint32_t* tile_counter, void* status, cudaStream_t stream, int io = 0) {
+                     const uint32_t* digit_base, uint32_t* tile_counter, void* status, void* next_status, cudaStream_t stream, int io = 0) {
     const bool small = count < kSmallSortLimit;
-    if (io == 1) return launch_pass<BigTile, StatusT, true, 1>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
-    if (io == 2) return launch_pass<BigTile, StatusT, true, 2>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
-    if (io == 3) return launch_pass<BigTile, StatusT, true, 3>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
+    if (io == 1) return launch_pass<BigTile, StatusT, true, 1>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, next_status, stream);
+    if (io == 2) return launch_pass<BigTile, StatusT, true, 2>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, next_status, stream);
+    if (io == 3) return launch_pass<BigTile, StatusT, true, 3>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, next_status, stream);
     if (vi != nullptr)
-        return small ? launch_pass<SmallTile, StatusT, true>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream)
-                     : launch_pass<BigTile, StatusT, true>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
-    return small ? launch_pass<SmallTile, StatusT, false>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream)
-                 : launch_pass<BigTile, StatusT, false>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, stream);
+        return small ? launch_pass<SmallTile, StatusT, true>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, next_status, stream)
+                     : launch_pass<BigTile, StatusT, true>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, next_status, stream);
+    return small ? launch_pass<SmallTile, StatusT, false>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, next_status, stream)
+                 : launch_pass<BigTile, StatusT, false>(ki, vi, ko, vo, count, shift, digit_base, tile_counter, status, next_status, stream);
 }
 
 }  // namespace
@@ -724,7 +728,8 @@ cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint3
     const uint64_t pass_bytes = status_words_bytes(count);
     if (events && (e = cudaEventRecord(events[0], stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s.hist, 0, kSortPasses * kRadix * 4, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(s.status, 0, kHeaderWords * 4 + kSortPasses * pass_bytes, stream)) != cudaSuccess) return e;
+    // tile counters + pass 0's look-back words; every pass clears the words of the pass that follows it
+    if ((e = cudaMemsetAsync(s.status, 0, kHeaderWords * 4 + pass_bytes, stream)) != cudaSuccess) return e;
 
     k_histogram<<<histogram_grid(count), kHistThreads, kHistSmemBytes, stream>>>(keys, count, s.hist);
     k_scan_histogram<<<1, kSortPasses * kRadix, 0, stream>>>(s.hist, nullptr, -1);
@@ -740,6 +745,7 @@ cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint3
     const bool pairs = vals != nullptr && count >= kPairsSortLimit && s.pairs_capacity >= count && count >= kSmallSortLimit;
     for (int pass = 0; pass < kSortPasses; ++pass) {               // bitOffset = 0, 8, 16, 24
         void* st = status0 + (uint64_t)pass * pass_bytes;
+        void* next = pass + 1 < kSortPasses ? status0 + (uint64_t)(pass + 1) * pass_bytes : nullptr;
         int io = 0;
         if (pairs) {
             uint32_t* x = reinterpret_cast<uint32_t*>(s.pairs_x); uint32_t* y = reinterpret_cast<uint32_t*>(s.pairs_y);
@@ -750,9 +756,9 @@ cudaError_t sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint3
             vo = vals;
         }
         if (wide_status(count))
-            e = run_pass<uint64_t>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream, io);
+            e = run_pass<uint64_t>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, next, stream, io);
         else
-            e = run_pass<uint32_t>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream, io);
+            e = run_pass<uint32_t>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, next, stream, io);
         if (e != cudaSuccess) return e;
         if (launches) *launches += 1;
         if (events && (e = cudaEventRecord(events[2 + pass], stream)) != cudaSuccess) return e;
@@ -773,12 +779,12 @@ inline uint64_t status_bytes64(uint64_t count) { return (uint64_t)num_tiles64(co
 
 template <typename StatusT, bool kHasValues>
 cudaError_t launch_pass64(const uint64_t* ki, const uint32_t* vi, uint64_t* ko, uint32_t* vo, uint64_t count, int shift,
-                          const uint32_t* digit_base, uint32_t* tile_counter, void* status, cudaStream_t stream) {
+                          const uint32_t* digit_base, uint32_t* tile_counter, void* status, void* next_status, cudaStream_t stream) {
     constexpr int smem = PassSmem<Tile64, kHasValues, 8>::kTotal;
     auto kern = k_onesweep<Tile64, StatusT, kHasValues, false, uint64_t>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     kern<<<num_tiles64(count), Tile64::kBlock, smem, stream>>>(ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter,
-                                                               static_cast<StatusT*>(status), pass_flags(), nullptr, nullptr);
+                                                               static_cast<StatusT*>(status), static_cast<StatusT*>(next_status), pass_flags(), nullptr, nullptr);
     return cudaGetLastError();
 }
 }  // namespace
@@ -813,7 +819,7 @@ cudaError_t sort_pairs64(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uin
     constexpr int kPasses = 2 * kSortPasses;
     const uint64_t pass_bytes = status_bytes64(count);
     if ((e = cudaMemsetAsync(s.hist, 0, kPasses * kRadix * 4, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(s.status, 0, kHeaderWords * 4 + kPasses * pass_bytes, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.status, 0, kHeaderWords * 4 + pass_bytes, stream)) != cudaSuccess) return e;
     cudaFuncSetAttribute(k_histogram64, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes);
     const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((count + kHistThreads - 1) / kHistThreads, 1), (uint64_t)kNumSMs);
     for (int half = 0; half < 2; ++half) {
@@ -829,13 +835,14 @@ cudaError_t sort_pairs64(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uin
     uint64_t* ko = keys_alt; uint32_t* vo = vals_alt;
     for (int pass = 0; pass < kPasses; ++pass) {                    // bitOffset = 0, 8, ..., 56
         void* st = status0 + (uint64_t)pass * pass_bytes;
+        void* next = pass + 1 < kPasses ? status0 + (uint64_t)(pass + 1) * pass_bytes : nullptr;
         const bool wide = wide_status(count);
         if (vi != nullptr)
-            e = wide ? launch_pass64<uint64_t, true>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream)
-                     : launch_pass64<uint32_t, true>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream);
+            e = wide ? launch_pass64<uint64_t, true>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, next, stream)
+                     : launch_pass64<uint32_t, true>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, next, stream);
         else
-            e = wide ? launch_pass64<uint64_t, false>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream)
-                     : launch_pass64<uint32_t, false>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, stream);
+            e = wide ? launch_pass64<uint64_t, false>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, next, stream)
+                     : launch_pass64<uint32_t, false>(ki, vi, ko, vo, count, pass * kRadixBits, s.hist + pass * kRadix, counters + pass, st, next, stream);
         if (e != cudaSuccess) return e;
         if (launches) *launches += 1;
         const uint64_t* tk = ki; const uint32_t* tv = vi;
@@ -864,9 +871,9 @@ cudaError_t partition_pass(const uint32_t* src_keys, const uint32_t* src_vals, u
     uint32_t* counters = static_cast<uint32_t*>(s.status);
     void* st = static_cast<char*>(s.status) + kHeaderWords * 4;
     if (wide_status(count))
-        e = run_pass<uint64_t>(src_keys, src_vals, dst_keys, dst_vals, count, bit_offset, s.hist + pass * kRadix, counters, st, stream);
+        e = run_pass<uint64_t>(src_keys, src_vals, dst_keys, dst_vals, count, bit_offset, s.hist + pass * kRadix, counters, st, nullptr, stream);
     else
-        e = run_pass<uint32_t>(src_keys, src_vals, dst_keys, dst_vals, count, bit_offset, s.hist + pass * kRadix, counters, st, stream);
+        e = run_pass<uint32_t>(src_keys, src_vals, dst_keys, dst_vals, count, bit_offset, s.hist + pass * kRadix, counters, st, nullptr, stream);
     if (launches) *launches += 3;
     return e;
 }
@@ -899,12 +906,12 @@ cudaError_t partition_scatter(const uint32_t* src_keys, const uint32_t* src_vals
         constexpr int smem = PassSmem<SmallTile, true>::kTotal;
         cudaFuncSetAttribute(k_onesweep<SmallTile, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         k_onesweep<SmallTile, uint32_t, true, true><<<num_tiles(count), SmallTile::kBlock, smem, stream>>>(
-            src_keys, src_vals, static_cast<uint32_t*>(nullptr), nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, pass_flags(), key_ptrs, val_ptrs);
+            src_keys, src_vals, static_cast<uint32_t*>(nullptr), nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, static_cast<uint32_t*>(nullptr), pass_flags(), key_ptrs, val_ptrs);
     } else {
         constexpr int smem = PassSmem<BigTile, true>::kTotal;
         cudaFuncSetAttribute(k_onesweep<BigTile, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         k_onesweep<BigTile, uint32_t, true, true><<<num_tiles(count), BigTile::kBlock, smem, stream>>>(
-            src_keys, src_vals, static_cast<uint32_t*>(nullptr), nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, pass_flags(), key_ptrs, val_ptrs);
+            src_keys, src_vals, static_cast<uint32_t*>(nullptr), nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, static_cast<uint32_t*>(nullptr), pass_flags(), key_ptrs, val_ptrs);
     }
     if (launches) *launches += 1;
     return cudaGetLastError();
