@@ -85,6 +85,10 @@ class ComputeBufferSorter {                                            // Comput
     static void Sort(usrt_context* ctx, std::vector<uint32_t>& keys, std::vector<uint32_t>& values) {
         check(ctx, usrt_sort_pairs_host(ctx, keys.data(), values.data(), keys.size()));
     }
+    // ComputeBufferSorter<ulong, uint>: GetRadix is generic over uint / ulong keys (:179-191)
+    static void Sort(usrt_context* ctx, std::vector<uint64_t>& keys, std::vector<uint32_t>& values) {
+        check(ctx, usrt_sort_pairs64_host(ctx, keys.data(), values.data(), keys.size()));
+    }
 
   private:
     usrt_context* ctx_;
