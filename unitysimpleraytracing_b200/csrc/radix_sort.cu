@@ -232,6 +232,10 @@ constexpr bool kFullWarpRank = USRT_RANK_TRUST_LANE_ORDER != 0;
 #define USRT_LOOKBACK_WINDOW 4
 #endif
 constexpr int kLookBack = USRT_LOOKBACK_WINDOW;   // predecessor status words in flight per look-back round trip
+#ifndef USRT_TICKET_ITER
+#define USRT_TICKET_ITER 8
+#endif
+constexpr int kTicketIter = USRT_TICKET_ITER;     // output-loop iteration at which a CTA draws its next tile ticket
 #ifndef USRT_PREFETCH_AHEAD
 #define USRT_PREFETCH_AHEAD 148
 #endif
@@ -288,26 +292,45 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-    // dynamic tile id: a tile only ever waits on tiles that already started => forward progress
-    if (tid == 0) *s_tile_id = atomicAdd(tile_counter, 1u);
+    // Persistent CTAs: each draws tile tickets from a counter until none is left. A tile only ever waits on tiles with
+    // lower tickets, which running CTAs hold => forward progress. The NEXT ticket is drawn in the middle of the current
+    // tile's output loop, so the counter's L2 round trip no longer sits at the head of a tile with nothing else of the CTA
+    // to run (0.266 -> 0.254 ms per 2^26-pair pass). Not earlier: tickets fix the order in which tiles expect each other's
+    // aggregates, and a ticket that is held for long before its tile starts makes every successor's look-back wait for it
+    // (drawn before the look-back: 0.272 ms, with the next tile's keys requested ahead as well: 0.297 ms).
+    const uint32_t total_tiles = (n + (uint32_t)kTile - 1u) / (uint32_t)kTile;
     if (kFullWarpRank && warp == 0) {
         // Canary: the fast ranking below relies on one property of this SM's shared-memory atomic unit -- the lanes of
         // ONE instruction that hit the same address are applied in ascending lane order. Test it here, on this SM,
         // with a 32-way and four 8-way conflicts; if it ever fails this CTA ranks its tile the order-independent way.
-        if (lane < 8) s_canary[lane] = 0u;
+        // The test itself must run as ONE instruction per atomic, i.e. with the warp converged: nothing lane-dependent
+        // may precede it (every lane clears a word; the ticket draw of thread 0 comes afterwards) -- a warp that reaches
+        // the atomics in two groups reports the second group out of order although the hardware did nothing wrong.
+        s_canary[lane & 7u] = 0u;
         __syncwarp();
         const uint32_t a = atomicAdd(s_canary + 0, 1u);
         const uint32_t b = atomicAdd(s_canary + 1 + (lane & 3u), 1u);
         __syncwarp();
         if (a != lane || b != (lane >> 2) || (flags & 1u)) s_canary[7] = 1u;
     }
+    if (tid == 0) s_tile_id[0] = atomicAdd(tile_counter, 1u);
+    // Item map. A ranking group (a whole warp, or a 16-lane half in the fully verified flavour) owns kLanes * IPT
+    // CONSECUTIVE keys of the tile, item i of its lane l being key group * kLanes * IPT + kLanes * i + l -- so (round,
+    // lane) order inside a group IS memory order, which is what makes the per-group ranks stable. With whole warps a
+    // load is one coalesced 128-byte line; with half-warp groups it touches two 64-byte segments.
+    const uint32_t gl = lane & (uint32_t)(kLanes - 1);                      // lane within its group
+    const uint32_t group = (uint32_t)kGroupsPerWarp * warp + (kGroupsPerWarp == 2 ? (lane >> 4) : 0u);
+    const uint32_t item0 = group * (uint32_t)(kLanes * kIPT) + gl;
+#pragma unroll 1
+    for (uint32_t it = 0;; ++it) {
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
 #pragma unroll
         for (int i = 0; i < SM::kTblBytes / 16 / kBlock; ++i) z[tid + i * kBlock] = make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
-    const uint32_t tile = *s_tile_id;
+    __syncthreads();                                            // also: every warp has left the previous tile's output loop
+    const uint32_t tile = s_tile_id[it & 1u];
+    if (tile >= total_tiles) break;
     const uint32_t tile_base = tile * (uint32_t)kTile;
     const uint32_t valid = min((uint32_t)kTile, n - tile_base);
     // every tile clears its row of the NEXT pass's look-back words (that pass starts after this kernel has finished):
@@ -333,13 +356,6 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
         }
     }
 
-    // Item map. A ranking group (a whole warp, or a 16-lane half in the fully verified flavour) owns kLanes * IPT
-    // CONSECUTIVE keys of the tile, item i of its lane l being key group * kLanes * IPT + kLanes * i + l -- so (round,
-    // lane) order inside a group IS memory order, which is what makes the per-group ranks stable. With whole warps a
-    // load is one coalesced 128-byte line; with half-warp groups it touches two 64-byte segments.
-    const uint32_t gl = lane & (uint32_t)(kLanes - 1);                      // lane within its group
-    const uint32_t group = (uint32_t)kGroupsPerWarp * warp + (kGroupsPerWarp == 2 ? (lane >> 4) : 0u);
-    const uint32_t item0 = group * (uint32_t)(kLanes * kIPT) + gl;
     KeyT key[kIPT];
     uint32_t val[kHasValues ? kIPT : 1];
 #pragma unroll
@@ -518,6 +534,8 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
     // coalesced runs out: slot p of the tile goes to global_off[digit] + p
 #pragma unroll
     for (int i = 0; i < kIPT; ++i) {
+        if (i == (kTicketIter < kIPT ? kTicketIter : 0) && tid == 0)
+            s_tile_id[(it + 1u) & 1u] = atomicAdd(tile_counter, 1u);            // next ticket; read after the loop-top barrier
         const uint32_t p = tid + (uint32_t)i * kBlock;
         if (p < valid) {
             if constexpr (kHasValues && !kWide) {
@@ -544,6 +562,7 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
             }
         }
     }
+    }   // next tile
 }
 
 // ---- multi-GPU bucket exchange: the landing plan, computed on the device --------------------------------------------
@@ -638,6 +657,8 @@ inline uint32_t pass_flags() {
     static const uint32_t f = getenv("USRT_FORCE_SLOW_RANK") != nullptr ? 1u : 0u;   // test hook: order-independent ranking everywhere
     return f;
 }
+// persistent CTAs: as many as fit on the GPU at once (or one per tile when there are fewer tiles)
+template <typename Cfg> inline uint32_t pass_grid(uint32_t tiles) { return std::min<uint32_t>(tiles, (uint32_t)(kNumSMs * Cfg::kCtasPerSM)); }
 inline uint64_t status_words_bytes(uint64_t count) { return (uint64_t)num_tiles(count) * kRadix * (wide_status(count) ? 8 : 4); }
 
 template <typename Cfg, typename StatusT, bool kHasValues, int kIO = 0>
@@ -646,7 +667,7 @@ cudaError_t launch_pass(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, ui
     constexpr int smem = PassSmem<Cfg, kHasValues>::kTotal;
     auto kern = k_onesweep<Cfg, StatusT, kHasValues, false, uint32_t, kIO>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    kern<<<num_tiles(count), Cfg::kBlock, smem, stream>>>(ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter,
+    kern<<<pass_grid<Cfg>(num_tiles(count)), Cfg::kBlock, smem, stream>>>(ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter,
                                                          static_cast<StatusT*>(status), static_cast<StatusT*>(next_status), pass_flags(), nullptr, nullptr);
     return cudaGetLastError();
 }
@@ -783,7 +804,7 @@ cudaError_t launch_pass64(const uint64_t* ki, const uint32_t* vi, uint64_t* ko, 
     constexpr int smem = PassSmem<Tile64, kHasValues, 8>::kTotal;
     auto kern = k_onesweep<Tile64, StatusT, kHasValues, false, uint64_t>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    kern<<<num_tiles64(count), Tile64::kBlock, smem, stream>>>(ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter,
+    kern<<<pass_grid<Tile64>(num_tiles64(count)), Tile64::kBlock, smem, stream>>>(ki, vi, ko, vo, (uint32_t)count, shift, digit_base, tile_counter,
                                                                static_cast<StatusT*>(status), static_cast<StatusT*>(next_status), pass_flags(), nullptr, nullptr);
     return cudaGetLastError();
 }
@@ -905,12 +926,12 @@ cudaError_t partition_scatter(const uint32_t* src_keys, const uint32_t* src_vals
     if (count < kSmallSortLimit) {
         constexpr int smem = PassSmem<SmallTile, true>::kTotal;
         cudaFuncSetAttribute(k_onesweep<SmallTile, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_onesweep<SmallTile, uint32_t, true, true><<<num_tiles(count), SmallTile::kBlock, smem, stream>>>(
+        k_onesweep<SmallTile, uint32_t, true, true><<<pass_grid<SmallTile>(num_tiles(count)), SmallTile::kBlock, smem, stream>>>(
             src_keys, src_vals, static_cast<uint32_t*>(nullptr), nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, static_cast<uint32_t*>(nullptr), pass_flags(), key_ptrs, val_ptrs);
     } else {
         constexpr int smem = PassSmem<BigTile, true>::kTotal;
         cudaFuncSetAttribute(k_onesweep<BigTile, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_onesweep<BigTile, uint32_t, true, true><<<num_tiles(count), BigTile::kBlock, smem, stream>>>(
+        k_onesweep<BigTile, uint32_t, true, true><<<pass_grid<BigTile>(num_tiles(count)), BigTile::kBlock, smem, stream>>>(
             src_keys, src_vals, static_cast<uint32_t*>(nullptr), nullptr, (uint32_t)count, bit_offset, nullptr, counters, st, static_cast<uint32_t*>(nullptr), pass_flags(), key_ptrs, val_ptrs);
     }
     if (launches) *launches += 1;
