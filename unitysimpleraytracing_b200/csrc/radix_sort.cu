@@ -166,12 +166,13 @@ __global__ void __launch_bounds__(kSortPasses * kRadix) k_scan_histogram(uint32_
 }
 
 // ---- one radix pass: rank + look-back + staged stable scatter ------------------------------------
-// Shared memory per CTA (dynamic; BigTile 97 KB => 2 CTAs per SM):
-//   s_tbl  [2 x warps][256] u32        32 KB   one word per (16-lane group, digit): running count (low 16 bits) and,
-//                                              during a ranking round, the lane bits of the group (high 16 bits);
-//                                              after the scan: first tile slot of that group's keys of that digit
-//   s_pairs [tile] x {key, value}      64 KB   the tile staged in digit order
-//   s_global_off[256], s_part[H][256], s_scan[warps], s_tile_id
+// Shared memory per CTA (dynamic; BigTile = 256 threads x 24 pairs: 58 KB => 3 CTAs per SM, 80 registers per thread):
+//   s_tbl  [groups][256] u32            8 KB   one word per (ranking group, digit); a group is a whole warp (default) or a
+//                                              16-lane half (fully verified flavour: twice the tables): the group's running
+//                                              count of that digit; after the scan: first tile slot of the group's keys of it
+//   s_pairs [tile] x {key, value}      48 KB   the tile staged in digit order
+//   s_global_off[256], s_part[H][256], s_scan[warps], s_tile_id[2] (this tile's and the next ticket), s_canary[8]
+// The CTAs are persistent (grid = SMs x CTAs per SM): each loops over tile tickets drawn from a global counter.
 //
 // Ranking ("how many keys of my digit precede mine in the tile") replaces the HLSL WavePrefixCountBits /
 // WavePrefixSum one-bit splits of LocalRadixSort.compute:29-91. A 16-lane group owns 16*IPT CONSECUTIVE keys of
@@ -642,10 +643,19 @@ __global__ void __launch_bounds__(kRadix) k_peer_scatter_plan(const uint32_t* __
     if (d <= (uint32_t)world && bounds_out != nullptr) bounds_out[d] = s_bounds[d];
 }
 
+// SM count of the current device (148 on B200); persistent grids are sized from it
+inline int sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+        cudaGetLastError();
+        return kNumSMs;
+    }
+    return sms;
+}
 inline uint32_t histogram_grid(uint64_t count) {
     cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes);   // per device, cheap
     const uint64_t vec_work = (count + 4 * kHistThreads - 1) / (4 * kHistThreads);
-    return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(vec_work, 1), (uint64_t)kNumSMs);
+    return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(vec_work, 1), (uint64_t)sm_count());
 }
 inline uint32_t tile_pairs(uint64_t count) { return count < kSmallSortLimit ? SmallTile::kTile : BigTile::kTile; }
 inline uint32_t num_tiles(uint64_t count) { return (uint32_t)((count + tile_pairs(count) - 1) / tile_pairs(count)); }
@@ -658,7 +668,7 @@ inline uint32_t pass_flags() {
     return f;
 }
 // persistent CTAs: as many as fit on the GPU at once (or one per tile when there are fewer tiles)
-template <typename Cfg> inline uint32_t pass_grid(uint32_t tiles) { return std::min<uint32_t>(tiles, (uint32_t)(kNumSMs * Cfg::kCtasPerSM)); }
+template <typename Cfg> inline uint32_t pass_grid(uint32_t tiles) { return std::min<uint32_t>(tiles, (uint32_t)(sm_count() * Cfg::kCtasPerSM)); }
 inline uint64_t status_words_bytes(uint64_t count) { return (uint64_t)num_tiles(count) * kRadix * (wide_status(count) ? 8 : 4); }
 
 template <typename Cfg, typename StatusT, bool kHasValues, int kIO = 0>
@@ -842,7 +852,7 @@ cudaError_t sort_pairs64(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uin
     if ((e = cudaMemsetAsync(s.hist, 0, kPasses * kRadix * 4, stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s.status, 0, kHeaderWords * 4 + pass_bytes, stream)) != cudaSuccess) return e;
     cudaFuncSetAttribute(k_histogram64, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes);
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((count + kHistThreads - 1) / kHistThreads, 1), (uint64_t)kNumSMs);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((count + kHistThreads - 1) / kHistThreads, 1), (uint64_t)sm_count());
     for (int half = 0; half < 2; ++half) {
         k_histogram64<<<grid, kHistThreads, kHistSmemBytes, stream>>>(reinterpret_cast<const uint2*>(keys), count, half,
                                                                        s.hist + half * kSortPasses * kRadix);
