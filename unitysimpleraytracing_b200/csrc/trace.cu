@@ -262,17 +262,39 @@ __device__ __forceinline__ void store_hit(usrt_raycast_result* out, size_t i, co
     reinterpret_cast<float4*>(out)[i] = make_float4(h.distance, __uint_as_float(h.triangleIndex), h.uv[0], h.uv[1]);
 }
 
-// One warp = an 8 x 4 pixel tile, one CTA = 4 warps = 16 x 8 pixels. Only on-screen pixels are traced
+// One warp = a 16 x 2 pixel tile, one CTA = 4 warps = 16 x 8 pixels. Only on-screen pixels are traced
 // (the reference dispatches (W/32+1) x (H/32+1) groups with no bounds guard, RaytracingMeshDrawer.cs:83).
+// Warp shapes measured on B200, strict mode (tools/trace_lab.py): configs[1] at 1080p 8x4 0.910 ms, 4x8 0.929, 16x2 0.881,
+// 32x1 0.867; configs[0] at 512x512 8x4 0.846, 4x8 0.824, 16x2 0.852, 32x1 0.922 -- scene dependent; 16x2 gains 3 % on
+// the headline scene and loses under 1 % on the soup, 32x1 loses 9 % there. Also measured there, none faster: deferred
+// siblings in shared memory (8-24 slots), 4- and 16-entry leaf FIFOs, register caps for 10 and 12 CTAs per SM.
+#ifndef USRT_TRACE_WARP_W
+#define USRT_TRACE_WARP_W 16                                      // lab switch: 8 (8x4), 4 (4x8), 16 (16x2), 32 (32x1)
+#endif
+#if USRT_TRACE_WARP_W == 32
+constexpr int kTileW = 32, kTileH = 4;
+#else
 constexpr int kTileW = 16, kTileH = 8;
+#endif
 
 template <bool kCulled>
 __global__ void __launch_bounds__(128) k_trace_primary(TraceScene scene, PrimaryParams p, usrt_raycast_result* __restrict__ out,
                                                        HitMirrors mirrors) {
     __shared__ uint32_t s_fifo[kCulled ? 1 : kLeafFifo][128];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+#if USRT_TRACE_WARP_W == 8
     const uint32_t x = blockIdx.x * kTileW + (warp & 1u) * 8u + (lane & 7u);
     const uint32_t row = blockIdx.y * kTileH + (warp >> 1) * 4u + (lane >> 3);
+#elif USRT_TRACE_WARP_W == 4
+    const uint32_t x = blockIdx.x * kTileW + warp * 4u + (lane & 3u);
+    const uint32_t row = blockIdx.y * kTileH + (lane >> 2);
+#elif USRT_TRACE_WARP_W == 32
+    const uint32_t x = blockIdx.x * kTileW + lane;
+    const uint32_t row = blockIdx.y * kTileH + warp;
+#else
+    const uint32_t x = blockIdx.x * kTileW + (lane & 15u);
+    const uint32_t row = blockIdx.y * kTileH + warp * 2u + (lane >> 4);
+#endif
     uint32_t y, out_row;
     bool valid = x < (uint32_t)p.width;
     if (p.num_shards > 0) {                                            // ray sharding: interleaved row blocks
