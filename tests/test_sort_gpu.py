@@ -125,6 +125,38 @@ def test_wide_look_back_words_path():
     assert out.returncode == 0 and "wide ok" in out.stdout, out.stderr[-2000:]
 
 
+def test_fast_ranking_path_is_the_one_that_runs():
+    """The pass kernel ranks with one returning shared-memory atomic per key and falls back to an order-independent
+    ballot ranking when its per-CTA canary fails. A canary that fails for the wrong reason (e.g. a compiler that
+    splits the warp before it) is silent: results stay correct, passes get ~1.8x slower. So time a 2^24-pair sort
+    in a fresh process with and without USRT_FORCE_SLOW_RANK (the hook that forces the fallback): the default must
+    be clearly faster, i.e. it is NOT running the fallback."""
+    import subprocess, sys, os
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from unitysimpleraytracing_b200 import host\n"
+        "n = 1 << 24; g = torch.Generator(device='cuda'); g.manual_seed(5)\n"
+        "k0 = torch.randint(0, 2**31 - 1, (n,), dtype=torch.int32, device='cuda', generator=g)\n"
+        "c = host.Context(2); s = torch.cuda.Stream(); c.set_stream(s.cuda_stream); ts = []\n"
+        "with torch.cuda.stream(s):\n"
+        "    for it in range(8):\n"
+        "        k = k0.clone(); v = torch.arange(n, dtype=torch.int32, device='cuda')\n"
+        "        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)\n"
+        "        a.record(s); c.sort_pairs_device(k.data_ptr(), v.data_ptr(), n); b.record(s); torch.cuda.synchronize()\n"
+        "        ts.append(a.elapsed_time(b))\n"
+        "assert bool((k[1:] >= k[:-1]).all())\n"
+        "print('ms', sorted(ts[3:])[2]); c.close()\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(extra):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **extra), capture_output=True, text=True)
+        assert out.returncode == 0 and "ms " in out.stdout, out.stderr[-2000:]
+        return float(out.stdout.split("ms ")[1].split()[0])
+
+    fast, slow = run({}), run({"USRT_FORCE_SLOW_RANK": "1"})
+    assert slow > 1.25 * fast, "default sort %.3f ms vs forced fallback %.3f ms: the fast ranking path is not being taken" % (fast, slow)
+
+
 def _exact_bucket_ranges(global_hist, world):
     """choose_bucket_ranges in exact integer arithmetic (the rule k_peer_scatter_plan implements)."""
     csum = [0]
