@@ -161,7 +161,11 @@ def cpu_step(ref_mod, tris, cam, rows, threads, keep_frame=False):
     t_build = time.perf_counter() - t0
     y0 = (H - rows) // 2
     t1 = time.perf_counter()
-    frame = scene.trace_primary(W, H, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], y0=y0, y1=y0 + rows, threads=threads)
+    frame = scene.trace_primary(W, H, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], y0=y0, y1=y0 + rows, threads=threads,
+                                counters=keep_frame)
+    counts = None
+    if keep_frame:                                  # oracle-counted work per ray, reported beside rays/s
+        frame, counts = frame
     t_trace_rows = time.perf_counter() - t1
     t_frame = t_trace_rows * (H / rows)
     out = dict(step_s=t_build + t_frame, build_s=t_build, trace_rows_s=t_trace_rows, trace_frame_s=t_frame, stages=tm,
@@ -169,6 +173,10 @@ def cpu_step(ref_mod, tris, cam, rows, threads, keep_frame=False):
     if keep_frame:
         out["frame"] = frame
         out["scene"] = scene
+        nr = float(rows * W)
+        out["work_per_ray"] = {"node_box_tests": float(counts[0]) / nr, "triangle_box_tests": float(counts[1]) / nr,
+                               "triangle_tests": float(counts[2]) / nr, "max_stack_depth": int(counts[3]),
+                               "note": "counted by the CPU oracle on the same frame (strict = the reference's walk: no culling)"}
     return out
 
 
@@ -453,12 +461,24 @@ def run_ours(args):
             ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=False)
             b.record(stream)
         torch.cuda.synchronize()
-        ctx.set_trace_mode(0)
         cu_ms = statistics.median(a.elapsed_time(b) for a, b in cu_ev)
         differ = int((strict_frame.view(np.uint32).reshape(-1, 4) != culled_frame.view(np.uint32).reshape(-1, 4)).any(1).sum())
         culled = {"ms": cu_ms, "mrays_s": rays / (cu_ms * 1e-3) / 1e6, "records_differing_from_strict": differ,
                   "note": "non-parity mode, not part of `value`"}
-        del strict_frame, culled_frame
+        # mode 2: culled + the nearer of two hit internal children first, also non-parity
+        ctx.set_trace_mode(2)
+        near_frame = ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=True)
+        nf_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
+        for i, (a, b) in enumerate(nf_ev):
+            flush.fill_(i & 0xFF); a.record(stream)
+            ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=False)
+            b.record(stream)
+        torch.cuda.synchronize()
+        ctx.set_trace_mode(0)
+        nf_ms = statistics.median(a.elapsed_time(b) for a, b in nf_ev)
+        culled["near_first"] = {"ms": nf_ms, "mrays_s": rays / (nf_ms * 1e-3) / 1e6, "records_differing_from_strict":
+                                int((strict_frame.view(np.uint32).reshape(-1, 4) != near_frame.view(np.uint32).reshape(-1, 4)).any(1).sum())}
+        del strict_frame, culled_frame, near_frame
     barrier()
 
     # ---- e2e: the same step through the C ABI with HOST buffers, on EVERY rank -------------------------------
@@ -616,6 +636,7 @@ def run_ours(args):
         cpu_value = rays / statistics.mean(s["step_s"] for s in cs) / 1e6
         # free check: the oracle's whole frame (rank 0's camera) against the frame the timed run left on the GPU
         checks["frame_vs_oracle_whole_frame"] = bool(cs[0]["frame"].tobytes() == gpu_frame.tobytes())
+        work_per_ray = cs[0]["work_per_ray"]
         sc = cs[0]["scene"]
         checks["build_buffers_vs_oracle"] = bool(
             np.array_equal(ctx.download(_lib.BUF_KEYS), sc.sortedMortonCodes) and
@@ -654,7 +675,7 @@ def run_ours(args):
                            "note": "same step on ONE context, L2 flushed (512 MiB write) between steps, one CUDA event pair per "
                                    "step on this rank (median); stages_ms add up to this"},
             "stages_ms": stages,
-            "trace_mrays_s": rays / (trace_ms * 1e-3) / 1e6, "trace_culled": culled,
+            "trace_mrays_s": rays / (trace_ms * 1e-3) / 1e6, "trace_work_per_ray": work_per_ray, "trace_culled": culled,
             "build_ms": rebuild_graph_ms, "build_ms_launch_by_launch": stages["total"],
             "sort": {"pairs": ns, "ms": s_ms, "mkeys_s": ns / (s_ms * 1e-3) / 1e6, "achieved_gbs": sort_gbs,
                      "frac_of_measured_peak": sort_gbs / peak_gbs, "frac_of_8tbs": sort_gbs / 8000.0,

@@ -232,7 +232,9 @@ int usrt_diffuse_rays_device(usrt_context* ctx, int width, int height, float nea
 int usrt_hits_device(usrt_context* ctx, void** dev_ptr, uint64_t* count);
 /* 0 = strict (default): the reference's visiting semantics exactly -- every box the ray line touches
  * is visited, no distance culling. 1 = culled: skips boxes entirely beyond the current closest hit;
- * NOT part of the parity contract (reported separately). */
+ * 2 = culled, and of two internal children that are both hit the nearer one is walked first (SURVEY.md 8f-4
+ * "distance-culled + near-first traversal"). Modes 1 and 2 are NOT part of the parity contract (reported
+ * separately): equally distant triangles can resolve to a different id than the reference's visiting order gives. */
 int usrt_set_trace_mode(usrt_context* ctx, int mode);
 
 /* ---- importing a finished BVH ------------------------------------------------------ */

@@ -241,18 +241,25 @@ def test_fitted_world_box_opt_in(usrt, oracle, name):
     ctx.close()
 
 
-def test_culled_mode_is_reported_separately(usrt, oracle):
-    """Mode 1 is NOT part of the parity contract; it must still find a hit wherever strict does, never
-    a farther one by more than fp noise. We only record how far it is from strict."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_culled_modes_are_reported_separately(usrt, oracle, mode):
+    """Modes 1 (distance-culled) and 2 (culled, near child first; SURVEY 8f-4) are NOT part of the parity contract;
+    they must still find a hit wherever strict does, at the same distance up to ties. We only bound how far the
+    triangle ids are from strict (equally distant triangles may resolve differently)."""
     tris = _mesh("c1"); cam = meshes.SCENE_SOUP_CAMERA
     d = usrt.RaytracingMeshDrawer(tris).Awake()
     strict = d.Update(128, 128, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
-    d.container.ctx.set_trace_mode(1)
+    d.container.ctx.set_trace_mode(mode)
     culled = d.Update(128, 128, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
     d.container.ctx.set_trace_mode(0)
     assert np.array_equal(strict["distance"] == oracle.max_float(), culled["distance"] == oracle.max_float())
     differing = int((strict["triangleIndex"] != culled["triangleIndex"]).sum())
     assert differing <= len(strict) // 1000
+    assert int((strict["distance"] != culled["distance"]).sum()) <= len(strict) // 1000
+    again = d.Update(128, 128, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    assert again.tobytes() == strict.tobytes()                      # back in strict mode
+    with pytest.raises(_lib.UsrtError):
+        d.container.ctx.set_trace_mode(3)
     d.OnDestroy()
 
 

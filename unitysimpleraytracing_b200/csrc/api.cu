@@ -838,7 +838,7 @@ int usrt_last_sort_ms(usrt_context* ctx, float out_ms[6]) {
 
 int usrt_set_trace_mode(usrt_context* ctx, int mode) {
     NEED_CTX(ctx);
-    if (mode != 0 && mode != 1) return fail(ctx, USRT_ERR_ARG, "trace mode must be 0 (strict) or 1 (culled)");
+    if (mode < 0 || mode > 2) return fail(ctx, USRT_ERR_ARG, "trace mode must be 0 (strict), 1 (culled) or 2 (culled, near child first)");
     ctx->trace_mode = mode;
     return USRT_OK;
 }

@@ -89,7 +89,10 @@ __device__ __forceinline__ void ray_triangle(const Ray& r, const float4 v0, cons
     }
 }
 
-template <bool kCulled>
+// kNearFirst (mode 2, with culling only): of two internal children that are both hit, the one the ray enters first is
+// walked first, so the closest hit is found early and more of the far side is culled. Neither culled mode is part of the
+// parity contract: ties between equally distant triangles can resolve differently from the reference's visiting order.
+template <bool kCulled, bool kNearFirst = false>
 __device__ __forceinline__ usrt_raycast_result traverse(const TraceScene& s, const Ray& ray) {
     usrt_raycast_result best;
     best.distance = max_float();                       // Raytracing.compute:129-131
@@ -133,7 +136,11 @@ __device__ __forceinline__ usrt_raycast_result traverse(const TraceScene& s, con
             ray_triangle(ray, __ldg(t + 0), __ldg(t + 1), __ldg(t + 2), best);
         }
         const bool lgo = lhit && !(lref & 0x80000000u), rgo = rhit && !(rref & 0x80000000u);
-        if (rgo) {
+        if (kNearFirst && lgo && rgo) {
+            const bool left_first = lentry < rentry;
+            stack[sp++] = left_first ? rref : lref;
+            index = left_first ? lref : rref;
+        } else if (rgo) {
             if (lgo) stack[sp++] = lref;
             index = rref;
         } else if (lgo) {
@@ -277,9 +284,10 @@ constexpr int kTileW = 32, kTileH = 4;
 constexpr int kTileW = 16, kTileH = 8;
 #endif
 
-template <bool kCulled>
+template <int kMode>                                              // 0 strict, 1 culled, 2 culled + near child first
 __global__ void __launch_bounds__(128) k_trace_primary(TraceScene scene, PrimaryParams p, usrt_raycast_result* __restrict__ out,
                                                        HitMirrors mirrors) {
+    constexpr bool kCulled = kMode != 0;
     __shared__ uint32_t s_fifo[kCulled ? 1 : kLeafFifo][128];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 #if USRT_TRACE_WARP_W == 8
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(128) k_trace_primary(TraceScene scene, Primary
     usrt_raycast_result h;
     if (kCulled) {
         if (!valid) return;
-        h = traverse<true>(scene, ray);
+        h = traverse<true, kMode == 2>(scene, ray);
     } else {
         h = traverse_strict(scene, ray, valid, s_fifo);               // whole warps stay together (warp votes inside)
         if (!valid) return;
@@ -322,9 +330,10 @@ __global__ void __launch_bounds__(128) k_trace_primary(TraceScene scene, Primary
         if (j < mirrors.count) store_hit(mirrors.ptr[j], (size_t)out_row * (size_t)p.width + x, h);
 }
 
-template <bool kCulled>
+template <int kMode>
 __global__ void __launch_bounds__(128) k_trace_rays(TraceScene scene, const float4* __restrict__ rays, uint64_t num_rays,
                                                     usrt_raycast_result* __restrict__ out) {
+    constexpr bool kCulled = kMode != 0;
     __shared__ uint32_t s_fifo[kCulled ? 1 : kLeafFifo][128];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < num_rays;
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(128) k_trace_rays(TraceScene scene, const floa
     usrt_raycast_result h;
     if (kCulled) {
         if (!valid) return;
-        h = traverse<true>(scene, r);
+        h = traverse<true, kMode == 2>(scene, r);
     } else {
         h = traverse_strict(scene, r, valid, s_fifo);
         if (!valid) return;
@@ -430,8 +439,9 @@ cudaError_t launch_trace_primary(const TraceScene& scene, const PrimaryParams& p
     const int rows = p.num_shards > 0 ? p.local_rows : p.y1 - p.y0;
     if (rows <= 0 || p.width <= 0) return cudaSuccess;
     const dim3 grid((p.width + kTileW - 1) / kTileW, (rows + kTileH - 1) / kTileH);
-    if (mode == 1) k_trace_primary<true><<<grid, 128, 0, stream>>>(scene, p, out, mirrors);
-    else k_trace_primary<false><<<grid, 128, 0, stream>>>(scene, p, out, mirrors);
+    if (mode == 2) k_trace_primary<2><<<grid, 128, 0, stream>>>(scene, p, out, mirrors);
+    else if (mode == 1) k_trace_primary<1><<<grid, 128, 0, stream>>>(scene, p, out, mirrors);
+    else k_trace_primary<0><<<grid, 128, 0, stream>>>(scene, p, out, mirrors);
     return cudaGetLastError();
 }
 
@@ -439,8 +449,9 @@ cudaError_t launch_trace_rays(const TraceScene& scene, const float4* rays, uint6
                               int mode, cudaStream_t stream) {
     if (num_rays == 0) return cudaSuccess;
     const uint32_t grid = (uint32_t)((num_rays + 127) / 128);
-    if (mode == 1) k_trace_rays<true><<<grid, 128, 0, stream>>>(scene, rays, num_rays, out);
-    else k_trace_rays<false><<<grid, 128, 0, stream>>>(scene, rays, num_rays, out);
+    if (mode == 2) k_trace_rays<2><<<grid, 128, 0, stream>>>(scene, rays, num_rays, out);
+    else if (mode == 1) k_trace_rays<1><<<grid, 128, 0, stream>>>(scene, rays, num_rays, out);
+    else k_trace_rays<0><<<grid, 128, 0, stream>>>(scene, rays, num_rays, out);
     return cudaGetLastError();
 }
 
