@@ -52,4 +52,12 @@ for n_ in (3001, 300001):                                  # small-tile and big-
     c.partition_scatter_device(kd.data_ptr(), vd.data_ptr(), n_, 24, kp.data_ptr(), vp.data_ptr()); c.sync()
     o = np.argsort(k >> 24, kind="stable")
     assert np.array_equal(ok_.cpu().numpy().view(np.uint32), k[o]) and np.array_equal(ov_.cpu().numpy().view(np.uint32), v[o])
+# round 2: persistent sort CTAs -- more tiles than resident CTAs (444 x 6144 / 296 x 4096 pairs), so every CTA loops
+# (tile tickets, shared-memory reuse from one tile to the next), 32- and 64-bit keys
+k = np.random.default_rng(4).integers(0, 2**32, 3000001, dtype=np.uint64).astype(np.uint32); v = np.arange(3000001, dtype=np.uint32)
+o = np.argsort(k, kind="stable"); kk, vv = k.copy(), v.copy(); c.sort_pairs_host(kk, vv)
+assert np.array_equal(kk, k[o]) and np.array_equal(vv, v[o])
+k64 = np.random.default_rng(5).integers(0, 2**63, 1500001, dtype=np.uint64); v = np.arange(1500001, dtype=np.uint32)
+o = np.argsort(k64, kind="stable"); kk, vv = k64.copy(), v.copy(); c.sort_pairs64_host(kk, vv)
+assert np.array_equal(kk, k64[o]) and np.array_equal(vv, v[o])
 print("sanitize workload ok")
