@@ -485,11 +485,15 @@ def run_ours(args):
     # Frames are pipelined over two contexts: frame i+1's upload (copy engine, PCIe) overlaps frame i's
     # kernels; every frame still pays its own 128 MiB upload and its own 33 MB of hit records, which the
     # trace kernel writes straight into the page-locked frame. The strictly synchronous form follows (rank 0).
-    pinned_tris = torch.from_numpy(tris.view(np.uint8).reshape(-1)).pin_memory()
-    tris_h = pinned_tris.numpy().view(tris.dtype)
+    # Host buffers come from the library (usrt_host_alloc = cudaHostAlloc): what a host without a CUDA binding would use.
+    # (A bare 128 MiB copy from such memory runs at 55.5 GB/s against 51.7 GB/s from a block pinned after the fact,
+    # tools/h2d_probe.py; the pipelined frame time is 2.55 ms = 52.6 GB/s either way.)
     E = ctxs[:2] if D >= 2 else [ctxs[0], host.Context(n, device=local_rank)]
-    pinned_hits = [torch.empty(rays * 16, dtype=torch.uint8).pin_memory() for _ in E]
-    hits_h = [p.numpy().view(hit_dtype) for p in pinned_hits]
+    pinned_tris = ctx.host_alloc(tris.nbytes)
+    pinned_tris[:] = tris.view(np.uint8).reshape(-1)
+    tris_h = pinned_tris.view(tris.dtype)
+    pinned_hits = [ctx.host_alloc(rays * 16) for _ in E]
+    hits_h = [p.view(hit_dtype) for p in pinned_hits]
     e2e_steps = max(8, min(K, 40))
 
     def e2e_run(k):
@@ -515,8 +519,9 @@ def run_ours(args):
 
     # the same pipeline with the ADDITIVE positions-only upload (usrt_upload_positions_async: 48 of the 128 bytes of every
     # Triangle, all the build and the traversal read) -- reported beside the full-struct number, not instead of it
-    pinned_pos = torch.from_numpy(np.ascontiguousarray(tris.view(np.float32).reshape(n, 32)[:, :12])).pin_memory()
-    pos_h = pinned_pos.numpy()
+    pinned_pos = ctx.host_alloc(n * 48)
+    pos_h = pinned_pos.view(np.float32).reshape(n, 12)
+    pos_h[:] = tris.view(np.float32).reshape(n, 32)[:, :12]
 
     def e2e_pos_run(k):
         for i in range(k):
@@ -543,7 +548,8 @@ def run_ours(args):
                                                                    hits_h[0].tobytes() == gpu_frame.tobytes())
     for c in E:
         c.upload_triangles(tris_h)         # back to the full-struct source for the legs below
-    del pinned_pos
+    ctx.host_free(pinned_pos)
+    del pinned_pos, pos_h
 
     line = None
     e2e_sync_ms = None
@@ -563,6 +569,9 @@ def run_ours(args):
         e2e_sync_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
     if D < 2:
         E[1].close()
+    del tris_h, hits_h
+    for p in [pinned_tris] + pinned_hits:
+        ctx.host_free(p)
     del pinned_tris, pinned_hits
     barrier()
 

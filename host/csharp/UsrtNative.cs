@@ -50,6 +50,9 @@ namespace Usrt
                                                                     [In] float[] cameraToWorldRowMajor, int y0, int y1, [Out] RaycastResult[] hostOut);
         // frame pipeline over two contexts: page-locked buffers (e.g. cudaHostAlloc'ed, or Marshal-pinned + cudaHostRegister)
         [DllImport(Lib)] public static extern int usrt_upload_triangles_async(IntPtr ctx, IntPtr pinnedTriangles, uint n);
+        // page-locked host memory without a CUDA binding on the C# side (cudaHostAlloc / cudaFreeHost behind the ABI)
+        [DllImport(Lib)] public static extern int usrt_host_alloc(IntPtr ctx, ulong bytes, out IntPtr hostPtr);
+        [DllImport(Lib)] public static extern int usrt_host_free(IntPtr ctx, IntPtr hostPtr);
         [DllImport(Lib)] public static extern int usrt_trace_primary_async(IntPtr ctx, int width, int height, float near, float tanHalfFov,
                                                                           [In] float[] cameraToWorldRowMajor, IntPtr pinnedHostOut);
         [DllImport(Lib)] public static extern int usrt_diffuse_rays_device(IntPtr ctx, int width, int height, float near, float tanHalfFov,

@@ -109,6 +109,14 @@ int usrt_upload_triangles(usrt_context* ctx, const usrt_triangle* host_triangles
 /* Same, asynchronous: host_triangles must be page-locked and stay untouched until usrt_sync (or a later
  * synchronising call) returns. With two contexts on one GPU, frame i+1's upload overlaps frame i's kernels. */
 int usrt_upload_triangles_async(usrt_context* ctx, const usrt_triangle* pinned_host_triangles, uint32_t n);
+/* Page-locked host memory for the ..._async entry points and for zero-copy frames (usrt_trace_primary with a pinned
+ * host_out): cudaHostAlloc / cudaFreeHost behind the ABI, so that a host without a CUDA binding (the C# P/Invoke host)
+ * can get it. (A bare 128 MiB copy from cudaHostAlloc memory measured 55.5 GB/s on B200 against 51.7 GB/s from a malloc
+ * block pinned after the fact; the pipelined frame time of bench.py is the same for both.) The buffer belongs to the
+ * process, not to the context;
+ * free it with usrt_host_free after the last call that uses it has been synchronised. */
+int usrt_host_alloc(usrt_context* ctx, uint64_t bytes, void** host_ptr);
+int usrt_host_free(usrt_context* ctx, void* host_ptr);
 /* ADDITIVE to the reference's SetData of whole Triangle structs (MeshBufferContainer.cs:150): positions only -- 12 floats
  * per triangle, exactly the first 48 bytes of usrt_triangle (a.xyz, pad, b.xyz, pad, c.xyz, pad). Those are the only bytes the
  * build and the traversal ever read, so an animated mesh can re-send 48 instead of 128 bytes per triangle per frame. The

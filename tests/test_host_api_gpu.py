@@ -350,3 +350,29 @@ def test_positions_only_upload_is_bit_identical_to_a_full_upload(usrt, oracle):
     with pytest.raises(_lib.UsrtError):
         ctx.upload_positions(np.zeros((30001, 12), np.float32))
     ctx.close()
+
+
+def test_library_pinned_buffers_feed_the_async_entry_points(usrt, oracle):
+    """usrt_host_alloc / usrt_host_free: page-locked memory behind the ABI (for hosts without a CUDA binding). The
+    async upload and the zero-copy frame accept it (they refuse pageable memory), results are the usual ones."""
+    tris = meshes.uniform_soup(3000, seed=21); cam = meshes.SCENE_SOUP_CAMERA
+    ctx = usrt.Context(len(tris))
+    buf = ctx.host_alloc(tris.nbytes)
+    buf[:] = tris.view(np.uint8).reshape(-1)
+    frame = ctx.host_alloc(64 * 48 * 16)
+    with pytest.raises(_lib.UsrtError):
+        ctx.upload_triangles_async(tris)                                   # pageable: refused, not staged
+    ctx.upload_triangles_async(buf.view(tris.dtype))
+    ctx.rebuild()
+    hits = frame.view(usrt.RaycastResult)
+    ctx.trace_primary_async(64, 48, cam["near"], cam["tan_half_fov"], cam["cam_to_world"], hits)
+    ctx.sync()
+    want = oracle.Scene(tris).trace_primary(64, 48, cam["near"], cam["tan_half_fov"], cam["cam_to_world"])
+    assert hits.tobytes() == want.tobytes()
+    del hits
+    ctx.host_free(frame)
+    with pytest.raises(ValueError):
+        ctx.host_free(frame)                                               # already given back
+    with pytest.raises(_lib.UsrtError):
+        ctx.host_alloc(0)
+    ctx.close()                                                            # frees `buf`, which nobody gave back

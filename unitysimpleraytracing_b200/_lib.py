@@ -33,6 +33,8 @@ SIGNATURES = {
     "usrt_triangles_length": (_c.c_uint32, [_P]),
     "usrt_upload_triangles": (_c.c_int, [_P, _P, _c.c_uint32]),
     "usrt_upload_triangles_async": (_c.c_int, [_P, _P, _c.c_uint32]),
+    "usrt_host_alloc": (_c.c_int, [_P, _c.c_uint64, _c.POINTER(_P)]),
+    "usrt_host_free": (_c.c_int, [_P, _P]),
     "usrt_upload_positions": (_c.c_int, [_P, _P, _c.c_uint32]),
     "usrt_upload_positions_async": (_c.c_int, [_P, _P, _c.c_uint32]),
     "usrt_set_triangles_device": (_c.c_int, [_P, _P, _c.c_uint32]),

@@ -400,6 +400,28 @@ int usrt_upload_triangles_async(usrt_context* ctx, const usrt_triangle* pinned_h
     return USRT_OK;
 }
 
+int usrt_host_alloc(usrt_context* ctx, uint64_t bytes, void** host_ptr) {
+    NEED_CTX(ctx);
+    if (!host_ptr || bytes == 0) return fail(ctx, USRT_ERR_ARG, "host_alloc: null pointer or zero size");
+    *host_ptr = nullptr;
+    if (int r = bind_device(ctx)) return r;
+    const cudaError_t e = cudaHostAlloc(host_ptr, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *host_ptr = nullptr;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? USRT_ERR_NOMEM : USRT_ERR_CUDA, "host_alloc(%llu bytes): %s",
+                    (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return USRT_OK;
+}
+
+int usrt_host_free(usrt_context* ctx, void* host_ptr) {
+    NEED_CTX(ctx);
+    if (!host_ptr) return USRT_OK;
+    CU(ctx, cudaFreeHost(host_ptr));
+    return USRT_OK;
+}
+
 int usrt_set_triangles_device(usrt_context* ctx, const void* dev_triangles, uint32_t n) {
     NEED_CTX(ctx);
     if (!dev_triangles || n > ctx->capacity) return fail(ctx, USRT_ERR_ARG, "set_triangles_device: n=%u capacity=%u", n, ctx->capacity);

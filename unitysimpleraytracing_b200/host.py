@@ -53,6 +53,9 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            for p in list(getattr(self, "_pinned", {}).values()):        # buffers of host_alloc nobody gave back
+                self._lib.usrt_host_free(self._h, ctypes.c_void_p(p))
+            self._pinned = {}
             self._lib.usrt_destroy(self._h)
             self._h = None
 
@@ -113,6 +116,25 @@ class Context:
     def upload_triangles(self, tris):
         tris = np.ascontiguousarray(tris, dtype=Triangle)
         self._check(self._lib.usrt_upload_triangles(self._h, _ptr(tris), len(tris)))
+
+    def host_alloc(self, nbytes):
+        """Page-locked host memory from the library (usrt_host_alloc = cudaHostAlloc) as a uint8 numpy array; give it
+        back with host_free(array) once nothing enqueued still uses it. Faster to upload from than pages pinned after the
+        fact, and the only way to get pinned memory for a host that has no CUDA binding of its own."""
+        p = ctypes.c_void_p()
+        self._check(self._lib.usrt_host_alloc(self._h, int(nbytes), ctypes.byref(p)))
+        buf = (ctypes.c_uint8 * int(nbytes)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p.value
+        return arr
+
+    def host_free(self, arr):
+        base = arr if isinstance(arr, int) else arr.ctypes.data
+        p = getattr(self, "_pinned", {}).pop(base, None)
+        if p is None:
+            raise ValueError("host_free: not a buffer of host_alloc")
+        self._check(self._lib.usrt_host_free(self._h, ctypes.c_void_p(p)))
 
     def upload_triangles_async(self, pinned_tris):
         """pinned_tris: a Triangle array over page-locked memory (e.g. a view of a torch pin_memory() tensor);
