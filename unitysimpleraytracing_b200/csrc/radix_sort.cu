@@ -324,245 +324,245 @@ k_onesweep(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_i
     const uint32_t item0 = group * (uint32_t)(kLanes * kIPT) + gl;
 #pragma unroll 1
     for (uint32_t it = 0;; ++it) {
-    {
-        uint4* z = reinterpret_cast<uint4*>(smem);
+        {
+            uint4* z = reinterpret_cast<uint4*>(smem);
 #pragma unroll
-        for (int i = 0; i < SM::kTblBytes / 16 / kBlock; ++i) z[tid + i * kBlock] = make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();                                            // also: every warp has left the previous tile's output loop
-    const uint32_t tile = s_tile_id[it & 1u];
-    if (tile >= total_tiles) break;
-    const uint32_t tile_base = tile * (uint32_t)kTile;
-    const uint32_t valid = min((uint32_t)kTile, n - tile_base);
-    // every tile clears its row of the NEXT pass's look-back words (that pass starts after this kernel has finished):
-    // one 1 KB store per tile instead of a memset over all passes' status before the sort
-    if (next_status != nullptr && tid < kRadix) next_status[(size_t)tile * kRadix + tid] = 0;
-    if (kPrefetchAhead > 0) {
-        // Ask L2 for a tile a little further down the input (tiles are handed out in order, so some CTA will want it
-        // soon): its own loads then hit L2 instead of waiting on DRAM at the start of a CTA, where nothing else of that
-        // CTA can run. Any distance from 64 to 300 tiles measures the same: 0.277 -> 0.264 ms per 2^26-pair pass.
-        const uint64_t ahead = (uint64_t)tile_base + (uint64_t)kPrefetchAhead * kTile;
-        if (ahead + kTile <= n) {
-            if constexpr (kInPairs) {
-                const char* p = reinterpret_cast<const char*>(reinterpret_cast<const uint2*>(keys_in) + ahead);
-                for (uint32_t b = tid * 128u; b < (uint32_t)kTile * 8u; b += kBlock * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
-            } else {
-                const char* p = reinterpret_cast<const char*>(keys_in + ahead);
-                for (uint32_t b = tid * 128u; b < (uint32_t)kTile * (uint32_t)sizeof(KeyT); b += kBlock * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
-                if (kHasValues) {
-                    const char* q = reinterpret_cast<const char*>(vals_in + ahead);
-                    for (uint32_t b = tid * 128u; b < (uint32_t)kTile * 4u; b += kBlock * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + b));
+            for (int i = 0; i < SM::kTblBytes / 16 / kBlock; ++i) z[tid + i * kBlock] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();                                            // also: every warp has left the previous tile's output loop
+        const uint32_t tile = s_tile_id[it & 1u];
+        if (tile >= total_tiles) break;
+        const uint32_t tile_base = tile * (uint32_t)kTile;
+        const uint32_t valid = min((uint32_t)kTile, n - tile_base);
+        // every tile clears its row of the NEXT pass's look-back words (that pass starts after this kernel has finished):
+        // one 1 KB store per tile instead of a memset over all passes' status before the sort
+        if (next_status != nullptr && tid < kRadix) next_status[(size_t)tile * kRadix + tid] = 0;
+        if (kPrefetchAhead > 0) {
+            // Ask L2 for a tile a little further down the input (tiles are handed out in order, so some CTA will want it
+            // soon): its own loads then hit L2 instead of waiting on DRAM at the start of a CTA, where nothing else of that
+            // CTA can run. Any distance from 64 to 300 tiles measures the same: 0.277 -> 0.264 ms per 2^26-pair pass.
+            const uint64_t ahead = (uint64_t)tile_base + (uint64_t)kPrefetchAhead * kTile;
+            if (ahead + kTile <= n) {
+                if constexpr (kInPairs) {
+                    const char* p = reinterpret_cast<const char*>(reinterpret_cast<const uint2*>(keys_in) + ahead);
+                    for (uint32_t b = tid * 128u; b < (uint32_t)kTile * 8u; b += kBlock * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+                } else {
+                    const char* p = reinterpret_cast<const char*>(keys_in + ahead);
+                    for (uint32_t b = tid * 128u; b < (uint32_t)kTile * (uint32_t)sizeof(KeyT); b += kBlock * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+                    if (kHasValues) {
+                        const char* q = reinterpret_cast<const char*>(vals_in + ahead);
+                        for (uint32_t b = tid * 128u; b < (uint32_t)kTile * 4u; b += kBlock * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + b));
+                    }
                 }
             }
         }
-    }
 
-    KeyT key[kIPT];
-    uint32_t val[kHasValues ? kIPT : 1];
-#pragma unroll
-    for (int i = 0; i < kIPT; ++i) {
-        const uint32_t idx = item0 + (uint32_t)i * kLanes;
-        if constexpr (kInPairs) {
-            const uint2 kv = idx < valid ? __ldg(reinterpret_cast<const uint2*>(keys_in) + tile_base + idx) : make_uint2(0xFFFFFFFFu, 0u);
-            key[i] = kv.x; val[i] = kv.y;
-        } else {
-            key[i] = idx < valid ? __ldg(keys_in + tile_base + idx) : ~(KeyT)0;  // tail pads sort last, never stored
-        }
-    }
-
-    // stable rank of every key among the keys of its group with the same digit, kPack to a register
-    uint32_t rankp[(kIPT + kPack - 1) / kPack];
-    uint32_t* tbl = s_tbl + group * kRadix;
-    auto put_rank = [&](int i, uint32_t r) {
-        if (i % kPack == 0) rankp[i / kPack] = r; else rankp[i / kPack] |= r << ((i % kPack) * kRankBits);
-    };
-    if constexpr (kFullWarpRank) {
-        if (s_canary[7] == 0u) {
-            // One returning atomic per key: old = keys of this digit in the warp's earlier rounds + the lower lanes of this
-            // round (ascending-lane serialisation, validated by the canary above) = the stable rank.
-#pragma unroll
-            for (int i = 0; i < kIPT; ++i) {
-                put_rank(i, atomicAdd(tbl + ((uint32_t)(key[i] >> shift) & 255u), 1u));
-                __syncwarp();                                   // rounds are ordered
-            }
-        } else {
-            uint16_t* s_rank = reinterpret_cast<uint16_t*>(smem + SM::kTblBytes);       // the staging area is still free
-            const KeyT* tile_keys = kInPairs ? reinterpret_cast<const KeyT*>(reinterpret_cast<const uint2*>(keys_in) + tile_base)
-                                             : keys_in + tile_base;
-            rank_warp_order_independent<KeyT, kInPairs>(tile_keys, valid, item0, kIPT, shift, tbl, s_rank);
-#pragma unroll
-            for (int i = 0; i < kIPT; ++i) put_rank(i, s_rank[item0 + (uint32_t)i * kLanes]);
-        }
-    } else {
-        // Fully verified flavour: the word also carries the lane bits of the round, so a lane sees which lanes of its group
-        // were applied before it; a higher lane among them sends the warp to the order-independent method.
-        const uint32_t add = (0x10000u << gl) | 1u, bit = 0x10000u << gl;
-        const uint32_t not_below = 0xFFFFu << gl;              // my own lane and the higher ones of my group
-        uint32_t out_of_order = flags & 1u;
-#pragma unroll
-        for (int i = 0; i < kIPT; ++i) {
-            const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
-            const uint32_t old = atomicAdd(tbl + d, add);
-            __syncwarp();
-            atomicSub(tbl + d, bit);
-            __syncwarp();
-            out_of_order |= (old >> 16) & not_below;
-            put_rank(i, old & 0xFFFFu);
-        }
-        if (__any_sync(0xFFFFFFFFu, out_of_order != 0u)) {
-            // Order-independent ranking (never taken on B200 unless forced): start the warp's two tables over.
-            uint32_t* mine = s_tbl + 2u * warp * kRadix;
-#pragma unroll
-            for (int i = 0; i < 2 * kRadix / 32; ++i) mine[lane + 32 * i] = 0u;
-            __syncwarp();
-            const uint32_t below = (1u << gl) - 1u;
-#pragma unroll
-            for (int i = 0; i < kIPT; ++i) {
-                const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
-                atomicAdd(tbl + d, add);
-                __syncwarp();
-                const uint32_t now = tbl[d];                    // every peer of this round has added itself
-                __syncwarp();
-                const uint32_t peers = now >> 16, total = now & 0xFFFFu;
-                const uint32_t before = __popc(peers & below);
-                if (before == 0) tbl[d] = total;                // the lowest peer clears the round's lane bits
-                __syncwarp();
-                put_rank(i, total - __popc(peers) + before);
-            }
-        }
-    }
-    __syncthreads();
-
-    // values are fetched now, so their latency hides behind the scan and the look-back below
-    if (kHasValues && !kInPairs) {
+        KeyT key[kIPT];
+        uint32_t val[kHasValues ? kIPT : 1];
 #pragma unroll
         for (int i = 0; i < kIPT; ++i) {
             const uint32_t idx = item0 + (uint32_t)i * kLanes;
-            val[i] = idx < valid ? __ldg(vals_in + tile_base + idx) : 0u;
-        }
-    }
-
-    // Scan step: kH threads per digit, each owning kGP consecutive groups. Thread (d, h) sums its groups' counts of
-    // digit d, the kH partial sums meet in s_part, every thread then knows the tile's count of d (published for the
-    // look-back right away) and the counts of the groups before its own.
-    const uint32_t d = tid & 255u, h = tid >> 8;
-    uint32_t cnt[kGP];
-    uint32_t part = 0;
-#pragma unroll
-    for (int j = 0; j < kGP; ++j) { cnt[j] = s_tbl[(h * kGP + j) * kRadix + d]; part += cnt[j]; }
-    if (kH > 1) {
-        s_part[h * kRadix + d] = part;
-        __syncthreads();
-    }
-    uint32_t count = 0, groups_before = 0;
-    if (kH > 1) {
-#pragma unroll
-        for (int k = 0; k < kH; ++k) {
-            const uint32_t v = s_part[k * kRadix + d];
-            count += v;
-            groups_before += (k < (int)h) ? v : 0u;
-        }
-    } else {
-        count = part;
-    }
-    StatusT* my_status = status + (size_t)tile * kRadix + d;
-    if (h == 0) ST::store(my_status, (tile == 0 ? ST::kPrefix : ST::kAggregate) | (StatusT)count);
-    // exclusive scan of the 256 digit counts (every h does it for itself: no extra barrier, the values are the same)
-    uint32_t incl = count;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= (uint32_t)o) incl += y;
-    }
-    if (lane == 31) s_scan[warp] = incl;
-    __syncthreads();
-    uint32_t tile_start;                                        // first tile-local slot of digit d
-    {
-        const uint32_t w0 = h * (kRadix / 32);                  // first warp of my h
-        uint32_t wbase = 0;
-#pragma unroll
-        for (int w = 0; w < kRadix / 32; ++w) wbase += (w0 + w < warp) ? s_scan[w0 + w] : 0u;
-        tile_start = wbase + incl - count;
-        // in place: the count of (group, d) becomes the first tile slot of that group's keys of digit d
-        uint32_t running = tile_start + groups_before;
-#pragma unroll
-        for (int j = 0; j < kGP; ++j) { s_tbl[(h * kGP + j) * kRadix + d] = running; running += cnt[j]; }
-    }
-    __syncthreads();
-
-    // stage the tile in digit order
-#pragma unroll
-    for (int i = 0; i < kIPT; ++i) {
-        const uint32_t dg = (uint32_t)(key[i] >> shift) & 255u;
-        const uint32_t slot = tbl[dg] + ((rankp[i / kPack] >> ((i % kPack) * kRankBits)) & ((1u << kRankBits) - 1u));
-        if constexpr (kHasValues && !kWide) {
-            s_pairs[slot] = make_uint2((uint32_t)key[i], val[i]);
-        } else {
-            s_keys[slot] = key[i];
-            if (kHasValues) s_vals[slot] = val[i];
-        }
-    }
-    // Look-back AFTER staging: the aggregate was published before the scan, so by now the preceding
-    // tiles have usually posted their inclusive prefixes and the walk resolves in one round trip.
-    if (h == 0) {
-        // decoupled look-back over the preceding tiles' counts of this digit, kLookBack tiles per round
-        // trip (the loads are independent; only the accumulation is ordered)
-        uint32_t exclusive = 0;
-        if (tile > 0) {
-            int32_t t = (int32_t)tile - 1;
-            bool done = false;
-            while (!done) {
-                StatusT sw[kLookBack];
-#pragma unroll
-                for (int k = 0; k < kLookBack; ++k)
-                    sw[k] = (t - k >= 0) ? ST::load(status + (size_t)(t - k) * kRadix + d) : (StatusT)ST::kPrefix;
-#pragma unroll
-                for (int k = 0; k < kLookBack; ++k) {
-                    if (!done) {
-                        while ((sw[k] & ST::kFlagMask) == 0) sw[k] = ST::load(status + (size_t)(t - k) * kRadix + d);
-                        exclusive += (uint32_t)(sw[k] & ST::kValueMask);
-                        done = (sw[k] & ST::kPrefix) != 0;
-                    }
-                }
-                t -= kLookBack;
+            if constexpr (kInPairs) {
+                const uint2 kv = idx < valid ? __ldg(reinterpret_cast<const uint2*>(keys_in) + tile_base + idx) : make_uint2(0xFFFFFFFFu, 0u);
+                key[i] = kv.x; val[i] = kv.y;
+            } else {
+                key[i] = idx < valid ? __ldg(keys_in + tile_base + idx) : ~(KeyT)0;  // tail pads sort last, never stored
             }
-            ST::store(my_status, ST::kPrefix | (StatusT)(exclusive + count));
         }
-        s_global_off[d] = (kPeer ? 0u : digit_base[d]) + exclusive - tile_start;   // wraps mod 2^32 by design
-    }
-    __syncthreads();
 
-    // coalesced runs out: slot p of the tile goes to global_off[digit] + p
+        // stable rank of every key among the keys of its group with the same digit, kPack to a register
+        uint32_t rankp[(kIPT + kPack - 1) / kPack];
+        uint32_t* tbl = s_tbl + group * kRadix;
+        auto put_rank = [&](int i, uint32_t r) {
+            if (i % kPack == 0) rankp[i / kPack] = r; else rankp[i / kPack] |= r << ((i % kPack) * kRankBits);
+        };
+        if constexpr (kFullWarpRank) {
+            if (s_canary[7] == 0u) {
+                // One returning atomic per key: old = keys of this digit in the warp's earlier rounds + the lower lanes of this
+                // round (ascending-lane serialisation, validated by the canary above) = the stable rank.
 #pragma unroll
-    for (int i = 0; i < kIPT; ++i) {
-        if (i == (kTicketIter < kIPT ? kTicketIter : 0) && tid == 0)
-            s_tile_id[(it + 1u) & 1u] = atomicAdd(tile_counter, 1u);            // next ticket; read after the loop-top barrier
-        const uint32_t p = tid + (uint32_t)i * kBlock;
-        if (p < valid) {
-            if constexpr (kHasValues && !kWide) {
-                const uint2 kv = s_pairs[p];
-                const uint32_t dg = (kv.x >> shift) & 255u;
-                const uint32_t dst = s_global_off[dg] + p;
-                if (kPeer) {
-                    const unsigned long long kp = __ldg(key_ptrs + dg), vp = __ldg(val_ptrs + dg);
-                    if (kp != 0ull) {                          // null plan = a receive buffer would overflow: write nothing
-                        reinterpret_cast<uint32_t*>(kp)[dst] = kv.x;
-                        reinterpret_cast<uint32_t*>(vp)[dst] = kv.y;
-                    }
-                } else if (kOutPairs) {
-                    reinterpret_cast<uint2*>(keys_out)[dst] = kv;
-                } else {
-                    keys_out[dst] = kv.x;
-                    vals_out[dst] = kv.y;
+                for (int i = 0; i < kIPT; ++i) {
+                    put_rank(i, atomicAdd(tbl + ((uint32_t)(key[i] >> shift) & 255u), 1u));
+                    __syncwarp();                                   // rounds are ordered
                 }
             } else {
-                const KeyT k = s_keys[p];
-                const uint32_t dst = s_global_off[(uint32_t)(k >> shift) & 255u] + p;
-                keys_out[dst] = k;
-                if (kHasValues) vals_out[dst] = s_vals[p];
+                uint16_t* s_rank = reinterpret_cast<uint16_t*>(smem + SM::kTblBytes);       // the staging area is still free
+                const KeyT* tile_keys = kInPairs ? reinterpret_cast<const KeyT*>(reinterpret_cast<const uint2*>(keys_in) + tile_base)
+                                                 : keys_in + tile_base;
+                rank_warp_order_independent<KeyT, kInPairs>(tile_keys, valid, item0, kIPT, shift, tbl, s_rank);
+#pragma unroll
+                for (int i = 0; i < kIPT; ++i) put_rank(i, s_rank[item0 + (uint32_t)i * kLanes]);
+            }
+        } else {
+            // Fully verified flavour: the word also carries the lane bits of the round, so a lane sees which lanes of its group
+            // were applied before it; a higher lane among them sends the warp to the order-independent method.
+            const uint32_t add = (0x10000u << gl) | 1u, bit = 0x10000u << gl;
+            const uint32_t not_below = 0xFFFFu << gl;              // my own lane and the higher ones of my group
+            uint32_t out_of_order = flags & 1u;
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) {
+                const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+                const uint32_t old = atomicAdd(tbl + d, add);
+                __syncwarp();
+                atomicSub(tbl + d, bit);
+                __syncwarp();
+                out_of_order |= (old >> 16) & not_below;
+                put_rank(i, old & 0xFFFFu);
+            }
+            if (__any_sync(0xFFFFFFFFu, out_of_order != 0u)) {
+                // Order-independent ranking (never taken on B200 unless forced): start the warp's two tables over.
+                uint32_t* mine = s_tbl + 2u * warp * kRadix;
+#pragma unroll
+                for (int i = 0; i < 2 * kRadix / 32; ++i) mine[lane + 32 * i] = 0u;
+                __syncwarp();
+                const uint32_t below = (1u << gl) - 1u;
+#pragma unroll
+                for (int i = 0; i < kIPT; ++i) {
+                    const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+                    atomicAdd(tbl + d, add);
+                    __syncwarp();
+                    const uint32_t now = tbl[d];                    // every peer of this round has added itself
+                    __syncwarp();
+                    const uint32_t peers = now >> 16, total = now & 0xFFFFu;
+                    const uint32_t before = __popc(peers & below);
+                    if (before == 0) tbl[d] = total;                // the lowest peer clears the round's lane bits
+                    __syncwarp();
+                    put_rank(i, total - __popc(peers) + before);
+                }
             }
         }
-    }
+        __syncthreads();
+
+        // values are fetched now, so their latency hides behind the scan and the look-back below
+        if (kHasValues && !kInPairs) {
+#pragma unroll
+            for (int i = 0; i < kIPT; ++i) {
+                const uint32_t idx = item0 + (uint32_t)i * kLanes;
+                val[i] = idx < valid ? __ldg(vals_in + tile_base + idx) : 0u;
+            }
+        }
+
+        // Scan step: kH threads per digit, each owning kGP consecutive groups. Thread (d, h) sums its groups' counts of
+        // digit d, the kH partial sums meet in s_part, every thread then knows the tile's count of d (published for the
+        // look-back right away) and the counts of the groups before its own.
+        const uint32_t d = tid & 255u, h = tid >> 8;
+        uint32_t cnt[kGP];
+        uint32_t part = 0;
+#pragma unroll
+        for (int j = 0; j < kGP; ++j) { cnt[j] = s_tbl[(h * kGP + j) * kRadix + d]; part += cnt[j]; }
+        if (kH > 1) {
+            s_part[h * kRadix + d] = part;
+            __syncthreads();
+        }
+        uint32_t count = 0, groups_before = 0;
+        if (kH > 1) {
+#pragma unroll
+            for (int k = 0; k < kH; ++k) {
+                const uint32_t v = s_part[k * kRadix + d];
+                count += v;
+                groups_before += (k < (int)h) ? v : 0u;
+            }
+        } else {
+            count = part;
+        }
+        StatusT* my_status = status + (size_t)tile * kRadix + d;
+        if (h == 0) ST::store(my_status, (tile == 0 ? ST::kPrefix : ST::kAggregate) | (StatusT)count);
+        // exclusive scan of the 256 digit counts (every h does it for itself: no extra barrier, the values are the same)
+        uint32_t incl = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += y;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        uint32_t tile_start;                                        // first tile-local slot of digit d
+        {
+            const uint32_t w0 = h * (kRadix / 32);                  // first warp of my h
+            uint32_t wbase = 0;
+#pragma unroll
+            for (int w = 0; w < kRadix / 32; ++w) wbase += (w0 + w < warp) ? s_scan[w0 + w] : 0u;
+            tile_start = wbase + incl - count;
+            // in place: the count of (group, d) becomes the first tile slot of that group's keys of digit d
+            uint32_t running = tile_start + groups_before;
+#pragma unroll
+            for (int j = 0; j < kGP; ++j) { s_tbl[(h * kGP + j) * kRadix + d] = running; running += cnt[j]; }
+        }
+        __syncthreads();
+
+        // stage the tile in digit order
+#pragma unroll
+        for (int i = 0; i < kIPT; ++i) {
+            const uint32_t dg = (uint32_t)(key[i] >> shift) & 255u;
+            const uint32_t slot = tbl[dg] + ((rankp[i / kPack] >> ((i % kPack) * kRankBits)) & ((1u << kRankBits) - 1u));
+            if constexpr (kHasValues && !kWide) {
+                s_pairs[slot] = make_uint2((uint32_t)key[i], val[i]);
+            } else {
+                s_keys[slot] = key[i];
+                if (kHasValues) s_vals[slot] = val[i];
+            }
+        }
+        // Look-back AFTER staging: the aggregate was published before the scan, so by now the preceding
+        // tiles have usually posted their inclusive prefixes and the walk resolves in one round trip.
+        if (h == 0) {
+            // decoupled look-back over the preceding tiles' counts of this digit, kLookBack tiles per round
+            // trip (the loads are independent; only the accumulation is ordered)
+            uint32_t exclusive = 0;
+            if (tile > 0) {
+                int32_t t = (int32_t)tile - 1;
+                bool done = false;
+                while (!done) {
+                    StatusT sw[kLookBack];
+#pragma unroll
+                    for (int k = 0; k < kLookBack; ++k)
+                        sw[k] = (t - k >= 0) ? ST::load(status + (size_t)(t - k) * kRadix + d) : (StatusT)ST::kPrefix;
+#pragma unroll
+                    for (int k = 0; k < kLookBack; ++k) {
+                        if (!done) {
+                            while ((sw[k] & ST::kFlagMask) == 0) sw[k] = ST::load(status + (size_t)(t - k) * kRadix + d);
+                            exclusive += (uint32_t)(sw[k] & ST::kValueMask);
+                            done = (sw[k] & ST::kPrefix) != 0;
+                        }
+                    }
+                    t -= kLookBack;
+                }
+                ST::store(my_status, ST::kPrefix | (StatusT)(exclusive + count));
+            }
+            s_global_off[d] = (kPeer ? 0u : digit_base[d]) + exclusive - tile_start;   // wraps mod 2^32 by design
+        }
+        __syncthreads();
+
+        // coalesced runs out: slot p of the tile goes to global_off[digit] + p
+#pragma unroll
+        for (int i = 0; i < kIPT; ++i) {
+            if (i == (kTicketIter < kIPT ? kTicketIter : 0) && tid == 0)
+                s_tile_id[(it + 1u) & 1u] = atomicAdd(tile_counter, 1u);            // next ticket; read after the loop-top barrier
+            const uint32_t p = tid + (uint32_t)i * kBlock;
+            if (p < valid) {
+                if constexpr (kHasValues && !kWide) {
+                    const uint2 kv = s_pairs[p];
+                    const uint32_t dg = (kv.x >> shift) & 255u;
+                    const uint32_t dst = s_global_off[dg] + p;
+                    if (kPeer) {
+                        const unsigned long long kp = __ldg(key_ptrs + dg), vp = __ldg(val_ptrs + dg);
+                        if (kp != 0ull) {                          // null plan = a receive buffer would overflow: write nothing
+                            reinterpret_cast<uint32_t*>(kp)[dst] = kv.x;
+                            reinterpret_cast<uint32_t*>(vp)[dst] = kv.y;
+                        }
+                    } else if (kOutPairs) {
+                        reinterpret_cast<uint2*>(keys_out)[dst] = kv;
+                    } else {
+                        keys_out[dst] = kv.x;
+                        vals_out[dst] = kv.y;
+                    }
+                } else {
+                    const KeyT k = s_keys[p];
+                    const uint32_t dst = s_global_off[(uint32_t)(k >> shift) & 255u] + p;
+                    keys_out[dst] = k;
+                    if (kHasValues) vals_out[dst] = s_vals[p];
+                }
+            }
+        }
     }   // next tile
 }
 
