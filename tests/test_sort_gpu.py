@@ -68,6 +68,25 @@ def test_sort_properties_at_scale(usrt, log2n, kind):
     assert np.array_equal(np.bincount(k >> 24, minlength=256), np.bincount(keys >> 24, minlength=256))
 
 
+@pytest.mark.parametrize("n", [444 * 6144 - 1, 444 * 6144, 444 * 6144 + 1, 2 * 444 * 6144 + 6143, (1 << 22) - 1, (1 << 22) + 6145])
+@pytest.mark.parametrize("kind", ["uniform", "low"])
+def test_persistent_tile_loop_boundaries(usrt, n, kind):
+    """The pass kernel's CTAs are persistent (148 SMs x 3 CTAs = 444 tiles of 6,144 pairs at a time): counts right at and
+    around whole multiples of the resident tile set, ragged last tiles, and both sides of the 2^22-pair switch to
+    interleaved records -- exact against a stable argsort."""
+    keys = _keys(kind, n, seed=n & 0xFFFF)
+    values = np.arange(n, dtype=np.uint32)
+    order = np.argsort(keys, kind="stable")
+    k, v = keys.copy(), values.copy()
+    ctx = usrt.Context(2)
+    ctx.sort_pairs_host(k, v)
+    kk = keys.copy()
+    ctx.sort_pairs_host(kk)                                            # keys only
+    ctx.close()
+    assert np.array_equal(k, keys[order]) and np.array_equal(v, order.astype(np.uint32))
+    assert np.array_equal(kk, keys[order])
+
+
 def test_partition_pass_is_stable_split_by_top_byte(usrt):
     import torch
     n = 200003
