@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kRefitBlock) k_construct_bvh(uint32_t n, const
         // a.w), so its padded box is recomputed from them with K1's exact operations
         // (MeshBufferContainer.cs:52-63) instead of gathering the 32-byte triangleAABB entry as well.
         const float4* t = vertices.base + (size_t)tri * vertices.stride;
-        float4 a = __ldg(t + 0), b = __ldg(t + 1), c = __ldg(t + 2);
+        float4 a = ldg_vertex(t + 0), b = ldg_vertex(t + 1), c = ldg_vertex(t + 2);
         bmin = make_float4(__fsub_rn(sel_min(sel_min(a.x, b.x), c.x), 0.001f), __fsub_rn(sel_min(sel_min(a.y, b.y), c.y), 0.001f),
                            __fsub_rn(sel_min(sel_min(a.z, b.z), c.z), 0.001f), 0.0f);
         bmax = make_float4(__fadd_rn(sel_max(sel_max(a.x, b.x), c.x), 0.001f), __fadd_rn(sel_max(sel_max(a.y, b.y), c.y), 0.001f),
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) k_pack_traversal(uint32_t n, const uint32
     if (i < n) {                                                       // leaf slot i -> triangle copy in leaf order
         const uint32_t tri = __ldg(sorted_indices + i);
         const float4* t = tris + (size_t)tri * 8;
-        float4 a = __ldg(t + 0), b = __ldg(t + 1), c = __ldg(t + 2);
+        float4 a = ldg_vertex(t + 0), b = ldg_vertex(t + 1), c = ldg_vertex(t + 2);
         a.w = __uint_as_float(tri); b.w = 0.0f; c.w = 0.0f;
         packed_tris[(size_t)i * 3 + 0] = a; packed_tris[(size_t)i * 3 + 1] = b; packed_tris[(size_t)i * 3 + 2] = c;
     }

@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256) k_diffuse_rays(PrimaryParams p, const usr
         const float t = h.x;
         const float px = add(r.ox, mul(r.dx, t)), py = add(r.oy, mul(r.dy, t)), pz = add(r.oz, mul(r.dz, t));
         const float4* tri = vertices.base + (size_t)__float_as_uint(h.y) * vertices.stride;
-        const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+        const float4 a = ldg_vertex(tri), b = ldg_vertex(tri + 1), c = ldg_vertex(tri + 2);
         const float e1x = sub(b.x, a.x), e1y = sub(b.y, a.y), e1z = sub(b.z, a.z);
         const float e2x = sub(c.x, a.x), e2y = sub(c.y, a.y), e2z = sub(c.z, a.z);
         float nx = sub(mul(e1y, e2z), mul(e1z, e2y));

@@ -68,6 +68,19 @@ struct WorldBox { float min[3], max[3]; };            // NormalizeCentroid's box
 // Where K1 reads the three vertices of triangle i: base + i * stride float4s, a / b / c in slots 0..2. stride 8 = the
 // reference's 128-byte Triangle array; stride 3 = the compact 48-byte position records (usrt_upload_positions).
 struct VertexSource { const float4* base; uint32_t stride; };
+// One 16-byte vertex slot of a Triangle record. The build reads the first 48 of a record's 128 bytes: asking L2 to fetch
+// 64 bytes around the access instead of the default 128-byte line halves the DRAM reads of K1 / K5 on the Triangle array.
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 ldg_vertex(const float4* p) {
+#ifdef USRT_NO_L2_64B
+    return __ldg(p);
+#else
+    float4 v;
+    asm volatile("ld.global.nc.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#endif
+}
+#endif
 // (Measured: letting K1 also EMIT compact records for K5 costs more than it saves -- K1 34.6 -> 43.0 us for 48 MB of extra
 // writes against K5 102.4 -> 96.3 us at 1M triangles -- so K1, K5 and the bounce-ray generator all read whichever source
 // the caller uploaded.)
