@@ -27,6 +27,23 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
         ctx.set_trace_mode(0)
         out[name + "_sha"] = hashlib.sha256(ctx.trace_primary(W, H, cam["near"], cam["tan_half_fov"], cam["cam_to_world"]).tobytes()).hexdigest()[:16]
         ctx.close()
+    # incoherent rays over a 2^22-triangle soup (268 MB of packed nodes: beyond L2), strict and culled
+    tris = meshes.uniform_soup(1 << 22, seed=0x5EED0004)
+    rays = torch.from_numpy(meshes.incoherent_rays(1 << 20, seed=9)).cuda()
+    outb = torch.empty((1 << 20) * 4, dtype=torch.float32, device="cuda")
+    ctx = host.Context(len(tris)); ctx.upload_triangles(tris); ctx.rebuild(); ctx.sync()
+    s = torch.cuda.Stream(); ctx.set_stream(s.cuda_stream)
+    for mode in (0, 1):
+        ctx.set_trace_mode(mode)
+        with torch.cuda.stream(s):
+            ctx.trace_rays_device(rays.data_ptr(), 1 << 20, outb.data_ptr())
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+            for a, b in ev:
+                a.record(s); ctx.trace_rays_device(rays.data_ptr(), 1 << 20, outb.data_ptr()); b.record(s)
+        torch.cuda.synchronize()
+        out["inc_mode%d_ms" % mode] = float(np.median([a.elapsed_time(b) for a, b in ev]))
+        if mode == 0: out["inc_sha"] = hashlib.sha256(outb.cpu().numpy().tobytes()).hexdigest()[:16]
+    ctx.close()
     print(json.dumps(out))
     sys.exit(0)
 base = None
@@ -37,7 +54,7 @@ for lib in ["default"] + sys.argv[1:]:
         print(lib, "FAILED", r.stderr[-500:]); continue
     d = json.loads(line[0])
     if base is None: base = d
-    same = d["c2_sha"] == base["c2_sha"] and d["c1_sha"] == base["c1_sha"]
-    print("%-34s c2 strict %.4f ms (%.0f Mrays/s) culled %.4f | c1 strict %.4f culled %.4f | frames %s" % (
+    same = d["c2_sha"] == base["c2_sha"] and d["c1_sha"] == base["c1_sha"] and d["inc_sha"] == base["inc_sha"]
+    print("%-34s c2 strict %.4f ms (%.0f Mrays/s) culled %.4f | c1 strict %.4f culled %.4f | 2^22 soup, 2^20 incoherent rays strict %.2f culled %.2f | results %s" % (
         os.path.basename(lib), d["c2_mode0_ms"], 1920 * 1080 / d["c2_mode0_ms"] / 1e3, d["c2_mode1_ms"], d["c1_mode0_ms"], d["c1_mode1_ms"],
-        "identical" if same else "DIFFER"), flush=True)
+        d["inc_mode0_ms"], d["inc_mode1_ms"], "identical" if same else "DIFFER"), flush=True)

@@ -274,7 +274,9 @@ __device__ __forceinline__ void store_hit(usrt_raycast_result* out, size_t i, co
 // Warp shapes measured on B200, strict mode (tools/trace_lab.py): configs[1] at 1080p 8x4 0.910 ms, 4x8 0.929, 16x2 0.881,
 // 32x1 0.867; configs[0] at 512x512 8x4 0.846, 4x8 0.824, 16x2 0.852, 32x1 0.922 -- scene dependent; 16x2 gains 3 % on
 // the headline scene and loses under 1 % on the soup, 32x1 loses 9 % there. Also measured there, none faster: deferred
-// siblings in shared memory (8-24 slots), 4- and 16-entry leaf FIFOs, register caps for 10 and 12 CTAs per SM.
+// siblings in shared memory (8-24 slots), 4- and 16-entry leaf FIFOs, register caps for 10 and 12 CTAs per SM, and the
+// .L2::64B fetch-size qualifier on the node loads (0.879 -> 0.910 ms; incoherent rays over a 2^22-triangle soup 18.3 ->
+// 19.0 ms: the other half of a 128-byte line is the sibling node, i.e. a prefetch that pays) or on the triangle loads.
 #ifndef USRT_TRACE_WARP_W
 #define USRT_TRACE_WARP_W 16                                      // lab switch: 8 (8x4), 4 (4x8), 16 (16x2), 32 (32x1)
 #endif
