@@ -296,11 +296,23 @@ def run_ours(args):
     if exchange == "nccl":
         gathered = [torch.empty(world * rays * 4, dtype=torch.float32, device=dev) for _ in range(D)]
 
+    # A block starts from an idle GPU (barrier + synchronize). Left alone, the D streams then start in lockstep -- D
+    # rebuilds side by side, then D casts side by side, ... -- and may or may not drift apart within a short block (K = 20:
+    # 0.920 or 0.955 ms/step from one block to the next). So the first rebuild of stream j waits for the first rebuild of
+    # stream j-1: the streams enter the block staggered, the way a running pipeline is, and stay that way. Same work.
+    stagger = os.environ.get("USRT_BENCH_STAGGER", "1") != "0" and D > 1
+    first_rebuild_done = [None] * D
+
     def step(i):
         j = i % D
         c = ctxs[j]
         with torch.cuda.stream(streams[j]):
+            if stagger and 0 < i < D and first_rebuild_done[i - 1] is not None:
+                streams[j].wait_event(first_rebuild_done[i - 1])
             c.rebuild()
+            if stagger and i < D - 1:
+                first_rebuild_done[i] = torch.cuda.Event()
+                first_rebuild_done[i].record(streams[j])
             c.trace_primary(W, H, cam["near"], cam["tan_half_fov"], m, download=False)
             if peers is not None:
                 peers[j].fence()           # stream j resumes (step i+D) once every rank's frame i has landed everywhere
