@@ -263,12 +263,13 @@ def test_culled_modes_are_reported_separately(usrt, oracle, mode):
     d.OnDestroy()
 
 
-def test_large_soup_build_and_incoherent_rays(usrt, oracle):
-    """BASELINE config 4 shape at 2^22 triangles (the 2^24 run is recorded in profiles/): full build
+@pytest.mark.parametrize("log2n", [22, 24])
+def test_large_soup_build_and_incoherent_rays(usrt, oracle, log2n):
+    """BASELINE config 4 shape at 2^22 triangles and at its stated size, 2^24 = 16,777,216: full build
     parity by digest of every buffer, plus incoherent random rays and a small primary frame."""
     import hashlib
     sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
-    n = 1 << 22
+    n = 1 << log2n
     tris = meshes.uniform_soup(n, seed=0x5EED0004)
     ref = oracle.Scene(tris)
     ctx = usrt.Context(n)

@@ -87,6 +87,38 @@ def test_persistent_tile_loop_boundaries(usrt, n, kind):
     assert np.array_equal(kk, keys[order])
 
 
+@pytest.mark.parametrize("log2n", [28, 30])
+def test_device_sort_at_config3_sizes(usrt, log2n):
+    """BASELINE config 3 beyond 2^26: 2^28 and 2^30 pairs sorted in place on the device (2^30 is the first size that
+    uses the 64-bit look-back words), checked on the device: ascending keys, equal keys keep their input order (the
+    values are the input positions), every pair travelled together, the values are a permutation of 0..n-1."""
+    import torch
+    n = 1 << log2n
+    g = torch.Generator(device="cuda"); g.manual_seed(log2n)
+    keys = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda", generator=g)
+    keys[::5] >>= 20                                                   # plenty of duplicates: stability is exercised
+    orig = keys.clone()
+    vals = torch.arange(n, dtype=torch.int32, device="cuda")
+    ctx = usrt.Context(2)
+    ctx.sort_pairs_device(keys.data_ptr(), vals.data_ptr(), n)
+    ctx.sync()
+    chunk = 1 << 26
+    total = 0
+    for a in range(0, n, chunk):                                       # chunked so that temporaries stay small
+        b = min(n, a + chunk + 1)
+        k = keys[a:b].to(torch.int64) & 0xFFFFFFFF                     # the sorter orders keys as unsigned
+        v = vals[a:b].to(torch.int64) & 0xFFFFFFFF
+        assert bool((k[1:] >= k[:-1]).all())
+        assert bool(((v[1:] > v[:-1]) | (k[1:] != k[:-1])).all())
+        assert bool((orig[v[:-1] if b < n else v] == keys[a:b - 1 if b < n else b]).all())
+        total += int((v[:-1] if b < n else v).sum())
+    assert total == n * (n - 1) // 2
+    seen = torch.zeros(n, dtype=torch.bool, device="cuda")
+    seen[vals.to(torch.int64) & 0xFFFFFFFF] = True
+    assert bool(seen.all())
+    ctx.close()
+
+
 def test_partition_pass_is_stable_split_by_top_byte(usrt):
     import torch
     n = 200003
