@@ -54,6 +54,21 @@ def assemble_frame(gathered, width, height, num_shards, block_rows=8):
     return out.reshape((height * width,) + g.shape[3:])
 
 
+def _all_gather_into(out, mine, group=None):
+    """dist.all_gather_into_tensor -- or, on a backend without a CUDA all-gather (gloo: the single-GPU form of the GPU
+    tests, several processes sharing one device and talking through CUDA IPC), the same result from an all-reduce of a
+    buffer in which every rank fills its own slot. Only used for the small control messages (handles, histograms)."""
+    import torch.distributed as dist
+    if not (mine.is_cuda and dist.get_backend(group) == "gloo"):
+        dist.all_gather_into_tensor(out, mine, group=group)
+        return
+    r, m = dist.get_rank(group), mine.numel()
+    flat = out.view(-1)
+    flat.zero_()
+    flat[r * m:(r + 1) * m] = mine.reshape(-1)
+    dist.all_reduce(out, group=group)
+
+
 def map_peer_buffers(ctx, nbytes, group=None, device=None):
     """Allocate `nbytes` on this rank's GPU and map every other rank's buffer of the same call into this process
     (CUDA IPC over torch.distributed). Returns (own_ptr, [ptr of rank 0's buffer, ...]) with own_ptr at index
@@ -82,7 +97,7 @@ def map_peer_buffers(ctx, nbytes, group=None, device=None):
         raise RuntimeError("map_peer_buffers: allocation failed on some rank (this rank: %s)" % err)
     mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
     allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(allh, mine, group=group)
+    _all_gather_into(allh, mine, group=group)
     allh = allh.cpu().numpy().reshape(world, 64)
     peer_ptr = [0] * world
     peer_ptr[rank] = own_ptr
@@ -271,7 +286,7 @@ def dist_sort_pairs(keys_t, vals_t, group=None, local_partition=None, local_sort
     hist = hist.to(torch.int64)
     # 2. every rank learns every rank's histogram (256 x world int64: tiny)
     all_hist = torch.empty(world * 256, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_hist, hist.contiguous(), group=group)
+    _all_gather_into(all_hist, hist.contiguous(), group=group)
     all_hist = all_hist.view(world, 256).cpu().numpy()
     # 3. contiguous bucket ranges of ~equal mass, identical on every rank
     bounds = choose_bucket_ranges(all_hist.sum(0), world)
@@ -354,7 +369,7 @@ class PeerSortExchange:
         ctx.use_torch_stream()
         ctx.digit_histogram_device(keys_t.data_ptr(), n, 24, self._hist.data_ptr())
         # also the "receive buffers are free again" barrier: a rank gets here only after its previous local sort
-        dist.all_gather_into_tensor(self._all_hist, self._hist, group=self.group)
+        _all_gather_into(self._all_hist, self._hist, group=self.group)
         ctx.peer_scatter_plan_device(self._all_hist.data_ptr(), self.world, self.rank, self._peer_base.data_ptr(),
                                      self.capacity, self._ptrs.data_ptr(), self._ptrs.data_ptr() + 256 * 8,
                                      self._recv.data_ptr())
